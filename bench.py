@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/sec of merged output for the tiled-inference hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3              # this engine
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0   # the reference's torch-CPU path (oracle port)
+
+Workload (N=1): BASELINE configs[1] -- 5000x5000x3 uint8 image, 512x512 tiles stride 256 (361 tiles), D4 TTA
+(8 views), 4-class logits, pyramid weight. One "step" = one pass of the hot path over one image:
+    slice+augment kernel (image -> [8*361,3,512,512] f32)  +  fused de-augment/merge/normalise/crop kernel
+    ([8*361,4,512,512] f32 predictions -> [4,5000,5000] f32).
+The model between the two kernels is a black box that is NOT part of the path: the predictions are produced once
+before timing by the stand-in model of SURVEY 8(d) (`value`); `with_model` adds the stand-in kernel to the step.
+`e2e` goes through the public API (TiledInferenceEngine.predict) from a pinned HOST image to a pinned HOST result.
+Inputs per step (9.1 GB + 12.1 GB) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "megapixels/sec merged (5000x5000, 512 tiles, d4 TTA)"
+UNIT = "MP/s"
+CFG = dict(H=5000, W=5000, Cin=3, T=512, S=256, K=4, tta="d4", weight="pyramid")
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's torch-CPU path, restated by the oracle (the reference itself is
+# pure Python under /root/reference and cannot travel to the GPU box)
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(sample_tiles: int):
+    """Time the oracle's restatement of the reference loop (split -> augment -> stand-in model -> de-augment ->
+    integrate -> merge) on a bounded sample of cfg 2: the first `sample_tiles` of the 361 tiles (the whole-image
+    split and the full-canvas normalise are included in full). Returns (MP/s engine-only, MP/s with model, info)."""
+    from oracle import pipeline as OP
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    image = rng.integers(0, 256, (CFG["H"], CFG["W"], CFG["Cin"])).astype(np.uint8)
+    timings = {}
+    t0 = time.perf_counter()
+    OP.tiled_inference_cpu(image, CFG["T"], CFG["S"], CFG["K"], weight=CFG["weight"], group=CFG["tta"], batch_size=8,
+                           timings=timings, max_tiles=sample_tiles)
+    wall = time.perf_counter() - t0
+    n_total = 361
+    frac = sample_tiles / n_total
+    per_tile = timings["augment"] + timings["deaugment"] + timings["integrate"]
+    fixed = timings["split"] + timings["merge"]
+    # extrapolate the per-tile stages to all 361 tiles; whole-image stages are already complete
+    t_engine = fixed + per_tile / frac
+    t_with_model = t_engine + timings["model"] / frac
+    mp = CFG["H"] * CFG["W"] / 1e6
+    info = {
+        "cores": cores,
+        "kind": "port",
+        "sample": f"first {sample_tiles} of 361 tiles of cfg2 (d4, batch 8) through oracle/pipeline.py "
+                  f"(torch-CPU restatement of the reference loop); per-tile stages scaled x{1 / frac:.2f}, "
+                  f"whole-image split+normalise in full; wall {wall:.1f}s",
+        "stage_seconds_sample": {k: round(v, 3) for k, v in timings.items()},
+        "cpu_model": _cpu_model(),
+        "torch_threads": torch.get_num_threads(),
+    }
+    return mp / t_engine, mp / t_with_model, info
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    sample = args.cpu_sample_tiles
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_sample(8)
+    for _ in range(max(args.steps, 1)):
+        vals.append(cpu_reference_sample(sample))
+    eng = float(np.mean([v[0] for v in vals]))
+    info = vals[-1][2]
+    mp = CFG["H"] * CFG["W"] / 1e6
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": eng, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * mp / eng, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 5000x5000x3 u8, 512/256 tiles (361), d4 TTA, K=4, pyramid weight; "
+                               "torch-CPU reference loop, stand-in model excluded", "l2": "n/a (CPU)"},
+        "with_model": float(np.mean([v[1] for v in vals])),
+        "cpu_baseline": {"value": eng, "unit": UNIT, **{k: info[k] for k in ("cores", "kind", "sample")},
+                         "cpu_model": info["cpu_model"], "stage_seconds_sample": info["stage_seconds_sample"]},
+        "e2e": {"value": eng, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# this engine
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from pytorch_toolbelt_b200 import _native as N
+    from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine
+
+    rank, world, local = dist_env()
+    if world > 1:
+        from pytorch_toolbelt_b200.distributed.bench_multi import run_multi_gpu
+
+        return run_multi_gpu(args, CFG, METRIC, UNIT)
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    H, W, Cin, T, S, K = (CFG[k] for k in ("H", "W", "Cin", "T", "S", "K"))
+    rng = np.random.default_rng(0)
+    image_host = torch.from_numpy(rng.integers(0, 256, (H, W, Cin)).astype(np.uint8)).pin_memory()
+    eng = TiledInferenceEngine((H, W, Cin), T, S, channels=K, weight=CFG["weight"], tta=CFG["tta"])
+    A, n = eng.views, eng.num_tiles
+    Wm = torch.randn(K, Cin, generator=torch.Generator().manual_seed(0))
+    wm = (C.c_float * (K * Cin))(*[float(v) for v in Wm.flatten().tolist()])
+    stream = N.stream_ptr(dev)
+
+    def model(x, out=None):
+        y = out if out is not None else torch.empty((x.shape[0], K, T, T), dtype=torch.float32, device=dev)
+        N.check(N.lib().tb_standin_model(x.data_ptr(), x.shape[0], Cin, K, T, T, wm, y.data_ptr(), stream), "standin")
+        return y
+
+    image = image_host.to(dev)
+    aug = torch.empty((A * n, Cin, T, T), dtype=torch.float32, device=dev)   # 9.09 GB
+    pred = torch.empty((A * n, K, T, T), dtype=torch.float32, device=dev)    # 12.11 GB
+    out = torch.empty((K, H, W), dtype=torch.float32, device=dev)
+    eng.slice(image, out=aug)
+    model(aug, out=pred)
+    torch.cuda.synchronize()
+
+    def step(with_model=False):
+        eng.slice(image, out=aug)
+        if with_model:
+            model(aug, out=pred)
+        eng.merge(pred, out=out)
+
+    def timed(fn, steps):
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(steps):
+            fn()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / steps  # ms per step
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    torch.cuda.synchronize()
+
+    with ClockSampler(local) as clocks:
+        ms_step = timed(step, args.steps)
+        # per-kernel times on the same stream, same warm state (for the roofline of the dominant kernel)
+        ms_slice = timed(lambda: eng.slice(image, out=aug), args.steps)
+        ms_merge = timed(lambda: eng.merge(pred, out=out), args.steps)
+        ms_with_model = timed(lambda: step(True), args.steps)
+    clk = clocks.summary()
+
+    # ---- e2e through the public API with host buffers (pinned): H2D image, kernels + model, D2H result ----
+    out_host = torch.empty((K, H, W), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        res = eng.predict(image_host, model, batch_size=None)
+        out_host.copy_(res, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    ms_e2e = timed(e2e_step, max(2, args.steps // 2))
+
+    mp = H * W / 1e6
+    peak, peak_src = measured_peaks()
+    bytes_slice = H * W * Cin * 1 + n * A * Cin * T * T * 4
+    bytes_merge = n * A * K * T * T * 4 + K * H * W * 4
+    merge_gbs = bytes_merge / (ms_merge * 1e-3) / 1e9
+    slice_gbs = bytes_slice / (ms_slice * 1e-3) / 1e9
+
+    cpu_engine, cpu_with_model, cpu_info = cpu_reference_sample(args.cpu_sample_tiles)
+
+    line = {
+        "metric": METRIC, "value": mp / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "cfg2 (BASELINE configs[1]): 5000x5000x3 u8 -> 361 tiles 512/256 -> d4 TTA (8 views) -> "
+                        "K=4 logits merge, pyramid weight; engine-only (stand-in model excluded, predictions resident)",
+            "l2": "inputs (9.1 GB tiles out + 12.1 GB predictions in per step) >> 126 MB L2; no flush needed",
+            "kernels_per_step": ["slice_augment_kernel", "merge_all_kernel"],
+        },
+        "with_model": {"value": mp / (ms_with_model * 1e-3), "unit": UNIT, "ms_per_step": ms_with_model},
+        "e2e": {"value": mp / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": H * W * Cin, "d2h_bytes_per_step": K * H * W * 4,
+                "api": "TiledInferenceEngine.predict(pinned host image, model) -> pinned host [4,5000,5000] f32"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "merge_all_kernel", "achieved": merge_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": merge_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": bytes_merge, "ms": ms_merge},
+        "roofline_slice": {"bound": "hbm", "kernel": "slice_augment_kernel", "achieved": slice_gbs, "peak": peak,
+                           "unit": "GB/s", "frac": slice_gbs / peak, "algorithmic_bytes": bytes_slice, "ms": ms_slice},
+        "roofline_step": {"algorithmic_bytes": bytes_slice + bytes_merge,
+                          "achieved": (bytes_slice + bytes_merge) / (ms_step * 1e-3) / 1e9,
+                          "frac": (bytes_slice + bytes_merge) / (ms_step * 1e-3) / 1e9 / peak},
+        "cpu_baseline": {"value": cpu_engine, "unit": UNIT, "with_model": cpu_with_model, **cpu_info},
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-tiles", type=int, default=96)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

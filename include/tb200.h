@@ -1,0 +1,312 @@
+/*
+ * tb200.h -- C-ABI boundary of the B200 (sm_100a) tiled-inference / TTA / segmentation-loss engine.
+ *
+ * The reference (BloodAxe/pytorch-toolbelt @ 05e07ac, v0.8.0) is 100 % Python: it has no FFI. Its
+ * boundary for this path is the Python API of
+ *     pytorch_toolbelt/inference/tiles.py      (ImageSlicer :53, TileMerger :290)
+ *     pytorch_toolbelt/inference/tta.py        (*_image_augment / *_image_deaugment :257-524)
+ *     pytorch_toolbelt/inference/functional.py (flip / rot90 / transpose primitives :47-145, means :250-333)
+ *     pytorch_toolbelt/losses/functional.py    (focal :20, softmax focal :110, jaccard :188, dice :221, wing :250)
+ *     pytorch_toolbelt/losses/lovasz.py        (:23-160)
+ * Every entry point below names the reference lines whose ATen / NumPy / OpenCV work it replaces. The
+ * binding a maintainer would add is a ctypes stub; pytorch_toolbelt_b200/_native.py
+ * is that stub.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, <0 = argument error (TB_ERR_*), >0 = cudaError_t;
+ *     tb_last_error() returns a thread-local message for the last non-zero return on this thread;
+ *   - all data pointers are DEVICE pointers borrowed for the duration of the call unless the parameter
+ *     name ends in _host; the library never allocates, frees or retains caller-visible memory;
+ *   - every launch is asynchronous on the cudaStream_t passed as `stream` (void* here so that the header
+ *     needs no CUDA include) and does no implicit synchronisation;
+ *   - the caller selects the device (cudaSetDevice) before the call;
+ *   - no global mutable state besides one-time kernel-attribute setup: safe from several host threads.
+ */
+#ifndef TB200_H_
+#define TB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define TB_API __attribute__((visibility("default")))
+#else
+#define TB_API
+#endif
+
+/* ---- error codes (negative); positive values are cudaError_t ---- */
+#define TB_OK 0
+#define TB_ERR_ARG (-1)         /* bad argument value */
+#define TB_ERR_UNSUPPORTED (-2) /* combination not implemented by this build */
+#define TB_ERR_ALIGN (-3)       /* pointer / pitch alignment requirement violated */
+#define TB_ERR_WORKSPACE (-4)   /* caller workspace too small */
+
+/* ---- element types ---- */
+enum tb_dtype {
+  TB_U8 = 0,
+  TB_I8 = 1,
+  TB_U16 = 2,
+  TB_I16 = 3,
+  TB_I32 = 4,
+  TB_I64 = 5,
+  TB_F16 = 6,
+  TB_BF16 = 7,
+  TB_F32 = 8,
+  TB_F64 = 9
+};
+
+enum tb_layout { TB_HWC = 0, TB_CHW = 1 };
+
+/* TTA groups, views in the order the reference concatenates them (tta.py:269,284,333-341,410-420,484). */
+enum tb_tta {
+  TB_TTA_NONE = 0,   /* 1 view  */
+  TB_TTA_FLIPLR = 1, /* 2 views: id, lr                 tta.py:257-269 */
+  TB_TTA_FLIPUD = 2, /* 2 views: id, ud                 tta.py:272-284 */
+  TB_TTA_FLIPS = 3,  /* 3 views: id, lr, ud             tta.py:470-484 */
+  TB_TTA_D2 = 4,     /* 4 views: id, lr, ud, rot180     tta.py:319-341 */
+  TB_TTA_D4 = 5      /* 8 views (square tiles only)     tta.py:385-422 */
+};
+
+/* Same numeric values as OpenCV's cv2.BORDER_* (the reference forwards them to cv2.copyMakeBorder,
+ * tiles.py:161-169,182-190). */
+enum tb_border {
+  TB_BORDER_CONSTANT = 0,
+  TB_BORDER_REPLICATE = 1,
+  TB_BORDER_REFLECT = 2,
+  TB_BORDER_WRAP = 3,
+  TB_BORDER_REFLECT_101 = 4
+};
+
+/* _deaugment_averaging modes, tta.py:63-96 and functional.py:250-333. */
+enum tb_reduction {
+  TB_RED_NONE = 0, /* keep the A de-augmented views: out is [A,B,C,H,W] */
+  TB_RED_MEAN = 1,
+  TB_RED_SUM = 2,
+  TB_RED_GMEAN = 3,
+  TB_RED_HMEAN = 4,
+  TB_RED_HARMONIC1P = 5,
+  TB_RED_LOGODD = 6,
+  TB_RED_LOG1P = 7
+};
+
+/* Tile weight. TABLE reads the caller's [Th,Tw] array (bit-exact with TileMerger.weight, tiles.py:306);
+ * the analytic kinds regenerate the weight in registers (no memory traffic for it). */
+enum tb_weight_kind {
+  TB_W_TABLE = 0,
+  TB_W_ONES = 1,     /* "mean", tiles.py:282-283 */
+  TB_W_PYRAMID = 2,  /* compute_pyramid_patch_weight_loss, tiles.py:16-50; param = alpha (host float64 sum) */
+  TB_W_GAUSSIAN = 3  /* exp(-((i-(Th-1)/2)^2+(j-(Tw-1)/2)^2)/(2 sigma^2)); param = sigma (builder-defined) */
+};
+
+typedef struct tb_weight {
+  int kind;           /* enum tb_weight_kind */
+  const void* table;  /* device [Th,Tw], f32 (f64 for the f64 accumulator); TB_W_TABLE only */
+  double param;       /* alpha (PYRAMID) or sigma (GAUSSIAN) */
+} tb_weight;
+
+TB_API int tb_version(void);
+TB_API const char* tb_last_error(void);
+/* Number of views of a TTA group, or TB_ERR_ARG. */
+TB_API int tb_tta_views(int tta);
+
+/* ------------------------------------------------------------------------------------------------
+ * TILES
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Crop n tiles (native dtype, HWC) out of an HWC image with border synthesis.
+ * Replaces ImageSlicer.split / iter_split / cut_patch (tiles.py:144-234): NumPy slicing + cv2.copyMakeBorder.
+ *   img        [H,W,C] elements of elem_bytes (1,2,4,8)
+ *   xy         device int32 [n,2] = (x,y) of each tile in IMAGE frame (bbox_crops[:, :2]; may be negative)
+ *   clip_to_tile 0: border indices are remapped against the whole image (split semantics, tiles.py:182-190)
+ *                1: against the clipped tile extent (iter_split/cut_patch semantics, tiles.py:154-169)
+ *   border_value_host  4 x 8 bytes: per-channel raw element bits for channels 0..3 (cv2 Scalar); channels >=4 get 0
+ *   out        [n,Th,Tw,C] same element type
+ */
+TB_API int tb_crop_tiles(const void* img, int elem_bytes, int H, int W, int C, const int32_t* xy, int n, int Th,
+                  int Tw, int border_type, const uint64_t* border_value_host, int clip_to_tile, void* out,
+                  void* stream);
+
+/* Fused crop + HWC->CHW + cast to f32 (+ optional per-channel affine) + TTA augment.
+ * Replaces, per batch: ImageSlicer.split (tiles.py:177-204) -> image_to_tensor (utils/torch_utils.py:204-231)
+ * -> .float() -> tta.*_image_augment (tta.py:257-284,319-341,385-422,470-484).
+ *   img        [H,W,C] (TB_HWC) or [C,H,W] (TB_CHW); dtype TB_U8, TB_U16, TB_I16, TB_F16, TB_F32
+ *   xy         device int32 [n,2] image-frame (x,y)
+ *   scale_host / bias_host  NULL or C floats: out = float(src)*scale[c] + bias[c] (computed as mul then add)
+ *   out        f32 [A*n, C, Th, Tw], aug-major: row a*n + t  (torch.cat(dim=0) order)
+ */
+TB_API int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, int C, const int32_t* xy,
+                     int n, int Th, int Tw, int tta, int border_type, const float* border_value_host /*[4]*/,
+                     const float* scale_host, const float* bias_host, float* out, void* stream);
+
+/* Stand-alone TTA augment on [B,C,H,W] of any 1/2/4/8-byte element type (pure index permutation).
+ * Replaces tta.*_image_augment (tta.py:257-284,319-341,385-422,470-484) = flips/rot90s + torch.cat.
+ * out [A*B,C,H,W]. D4 requires H == W (tta.py:403-407). */
+TB_API int tb_tta_augment(const void* x, int elem_bytes, int B, int C, int H, int W, int tta, void* out, void* stream);
+
+/* One D4 element applied to `planes` planes of [H,W]: out[p,i,j] = x[p, map(i,j)] with
+ * view_code bit0 = transpose, bit1 = flip rows, bit2 = flip columns ((a,b) = transpose ? (j,i) : (i,j);
+ * si = flip_rows ? H-1-a : a; sj = flip_cols ? W-1-b : b). Transposing codes produce [W,H] planes.
+ * Replaces the primitives torch_fliplr/flipud/rot90_cw/rot90_ccw/rot180/transpose and their compositions
+ * (inference/functional.py:47-145). */
+TB_API int tb_view_permute(const void* x, int elem_bytes, int planes, int H, int W, int view_code, void* out,
+                           void* stream);
+
+/* Stand-alone TTA de-augment + reduction. Replaces tta.*_image_deaugment (tta.py:287-316,344-365,442-467,
+ * 503-524): chunk -> inverse flips/rot90s -> torch.stack -> _deaugment_averaging (tta.py:63-96).
+ *   x [A*B,C,H,W] (dtype TB_F32 or TB_F64); out [B,C,H,W], or [A,B,C,H,W] for TB_RED_NONE.
+ * Views are summed sequentially in view order 0..A-1 and MEAN divides by A (torch CPU semantics). */
+TB_API int tb_tta_deaugment(const void* x, int dtype, int B, int C, int H, int W, int tta, int reduction, void* out,
+                     void* stream);
+
+/* Streaming weighted scatter-accumulate of n tile predictions into the canvas, with the TTA de-augment
+ * fused in (tta = TB_TTA_NONE for plain TileMerger.integrate_batch).
+ * Replaces TileMerger.accumulate_single / integrate_batch (tiles.py:310-339) [+ tta.*_image_deaugment].
+ *   pred   [A*n,K,Th,Tw] dtype TB_F32 (accumulator f32) or TB_F64 (accumulator f64)
+ *   xy     int32 [n,2] canvas-frame (x,y) = crops[:, :2]; device pointer, or host pointer when
+ *          xy_is_host != 0 (n <= 64: passed by value in the kernel parameters, no copy)
+ *   image  [K,Hp,Wp], norm [Hp,Wp] (may be NULL): accumulated with float reductions (red.global.add);
+ *          tiles must lie inside the canvas
+ */
+TB_API int tb_deaugment_merge(const void* pred, int dtype, const int32_t* xy, int xy_is_host, int n, int K, int Th,
+                       int Tw, int tta, int reduction, const tb_weight* weight, void* image, void* norm,
+                       int Hp, int Wp, void* stream);
+
+/* merge(): out[k,i,j] = image[k,top+i,left+j] / norm[top+i,left+j]   (TileMerger.merge, tiles.py:345-350,
+ * fused with crop_to_orignal_size, tiles.py:271-280). dtype TB_F32 / TB_F64. out may alias image when
+ * top = left = 0, H = Hp, W = Wp (merge_). eps < 0: plain division (TileMerger); eps >= 0: the norm is
+ * clipped to eps first (ImageSlicer.merge, tiles.py:266). */
+TB_API int tb_normalize_crop(const void* image, const void* norm, int dtype, int K, int Hp, int Wp, int top, int left,
+                      int H, int W, double eps, void* out, void* stream);
+
+/* Regular tile grid: tile (r,c), r < ny, c < nx sits at canvas (x,y) = (c*Sx, r*Sy). Where its A*K
+ * prediction planes live:
+ *   default            rows a*n_slots + slot of `pred`, slot = tile_slot ? tile_slot[r*nx+c] : r*nx+c
+ *                      (slot < 0: tile absent);
+ *   tile_ptr != NULL   view 0 of tile t = r*nx+c starts at tile_ptr[t] ([K,Th,Tw] planes, f32; NULL: absent) and
+ *                      view a is tile_vstride[t] elements further per view: lets the caller merge the
+ *                      model's per-batch outputs ([A*b,K,Th,Tw] each, separate allocations) with no concat copy. */
+typedef struct tb_grid {
+  int nx, ny, Sx, Sy, Th, Tw;
+  int n_slots;                      /* tiles per view in pred (the aug-major stride) */
+  const int32_t* tile_slot;         /* device int32 [ny*nx] or NULL */
+  const float* const* tile_ptr;     /* device pointer table [ny*nx] or NULL */
+  const int64_t* tile_vstride;      /* device int64 [ny*nx]; required with tile_ptr */
+} tb_grid;
+
+/* Output-stationary fused de-augment + weighted merge + normalise + crop over a whole (or a row band of
+ * a) regular grid. Every CTA owns one canvas block, gathers the <= ceil(Th/Sy)*ceil(Tw/Sx) covering tile
+ * predictions in the reference's tile order (row-major over crops, tiles.py:132-139,337-339), accumulates
+ * in registers and writes each output pixel once: no atomics, no canvas read-modify-write, no norm_mask.
+ * Replaces the whole loop tta.*_image_deaugment -> TileMerger.integrate_batch -> merge -> crop
+ * (tta.py:442-467, tiles.py:321-350,271-280).
+ *   pred       f32 [A*n_slots,K,Th,Tw] (may be NULL when grid->tile_ptr is given)
+ *   rows       canvas rows [y0,y1) to produce (0,Hp for everything)
+ *   tile_rows  only tiles with r in [r0,r1) contribute (0,ny for everything)
+ *   init_num / init_den   NULL, or f32 [K,y1-y0,Wp] / [y1-y0,Wp] partial sums the accumulation starts from
+ *                         (halo received from the rank that owns the earlier tile rows)
+ *   raw != 0:  write un-normalised sums: out_num f32 [K,y1-y0,Wp], out_den f32 [y1-y0,Wp]; crop ignored
+ *   raw == 0:  write out f32 [K,H,W] rows (y-top) for y in [y0,y1) ∩ [top,top+H): out_num = out, out_den unused
+ */
+TB_API int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                 int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
+                 int raw, int top, int left, int H, int W, float* out_num, float* out_den, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LOSSES  (forward value + gradient w.r.t. the logits in one call)
+ * Layout for all of them: x is [B,C,inner] contiguous (inner = product of spatial dims).
+ * Workspaces: query the size with the *_workspace_bytes twin; contents need no initialisation.
+ * loss_out / stats_out are device pointers; the value is complete when the stream reaches that point.
+ * ---------------------------------------------------------------------------------------------- */
+
+enum tb_loss_reduction { TB_LOSS_NONE = 0, TB_LOSS_MEAN = 1, TB_LOSS_SUM = 2, TB_LOSS_BATCHWISE = 3 };
+enum tb_target_kind { TB_T_DENSE_F32 = 0, TB_T_LABELS_I64 = 1 };
+
+typedef struct tb_focal_params {
+  float gamma;
+  float alpha;             /* used when has_alpha */
+  int has_alpha;
+  float reduced_threshold; /* used when has_reduced_threshold */
+  int has_reduced_threshold;
+  float ignore_index;      /* compared against the float target; used when has_ignore */
+  int has_ignore;
+  int normalized;
+  float eps;               /* clamp_min of the normalisation factor (1e-6) */
+  int reduction;           /* enum tb_loss_reduction */
+  int softmax;             /* 0: p = sigmoid(x); 1: p = softmax over C (activation="softmax", softmax_dim=1) */
+} tb_focal_params;
+
+TB_API size_t tb_loss_workspace_bytes(int64_t B, int C, int64_t inner);
+
+/* Sigmoid (binary) focal loss. Replaces focal_loss_with_logits (losses/functional.py:19-107) and the
+ * one-hot expansion of BinaryFocalLoss (losses/focal.py:77-105) when t_kind = TB_T_LABELS_I64.
+ *   x f32 [B,C,inner]; t f32 [B,C,inner] or i64 [B,inner]; class_w NULL or f32 [C]
+ *   loss_out: f32 scalar (MEAN/SUM), [C,inner] (BATCHWISE) or [B,C,inner] (NONE)
+ *   grad: NULL or f32 [B,C,inner] = d(sum-reduced or mean-reduced scalar)/dx; for NONE/BATCHWISE it is the
+ *         per-element derivative d loss_e / d x_e (diagonal), not available with normalized
+ */
+TB_API int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C, int64_t inner,
+                     const tb_focal_params* p, const float* class_w, float* loss_out, float* grad, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* Softmax focal loss. Replaces softmax_focal_loss_with_logits (losses/functional.py:110-173).
+ *   x f32 [B,C,inner]; t i64 [B,inner]; ignore_index (int64) always active (default -100)
+ *   loss_out: scalar (MEAN/SUM), [inner] (BATCHWISE), [B,inner] (NONE) */
+TB_API int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C, int64_t inner, float gamma,
+                             float reduced_threshold, int has_reduced_threshold, int64_t ignore_index,
+                             int normalized, float eps, int reduction, const float* class_w, float* loss_out,
+                             float* grad, void* ws, size_t ws_bytes, void* stream);
+
+/* Dice / Jaccard. mode: 0 binary, 1 multiclass (softmax over C, i64 labels), 2 multilabel.
+ * Replaces DiceLoss.forward (losses/dice.py:59-131) / JaccardLoss.forward (losses/jaccard.py:48-103) and
+ * soft_dice_score / soft_jaccard_score (losses/functional.py:188-247).
+ * Phase 1 (stats): per class c: I = sum p*t, S = sum (p+t), Tsum = sum t over (B,inner) -> stats_out f64 [C,3]
+ * Phase 2 (loss + grad): loss_out f32 scalar; grad f32 [B,C,inner] (NULL to skip).
+ */
+typedef struct tb_dice_params {
+  int jaccard;       /* 0 dice, 1 jaccard */
+  int mode;          /* 0 binary, 1 multiclass, 2 multilabel */
+  int from_logits;
+  int log_loss;
+  float smooth;
+  float eps;
+  int has_ignore;    /* dice only (dice.py:85-111) */
+  float ignore_index;
+} tb_dice_params;
+
+TB_API int tb_dice_stats(const float* x, const void* t, int t_kind, int64_t B, int C, int64_t inner,
+                  const tb_dice_params* p, double* stats_out /*[C,3]*/, void* ws, size_t ws_bytes, void* stream);
+TB_API int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t B, int C, int64_t inner,
+                      const tb_dice_params* p, const double* stats /*[C,3]*/, const int32_t* classes /*NULL or [n_classes]*/,
+                      int n_classes, float* loss_out, float* grad, void* stream);
+
+/* Wing loss. Replaces wing_loss (losses/functional.py:250-277). reduction NONE/MEAN/SUM.
+ * grad = d loss / d x (NULL to skip); target gets no gradient here (shim negates for it). */
+TB_API int tb_wing_fwd_bwd(const float* x, const float* t, int64_t n, float width, float curvature, int reduction,
+                    float* loss_out, float* grad, void* ws, size_t ws_bytes, void* stream);
+
+/* Lovasz: given errors already sorted descending with their ground-truth bits (gt_sorted f32 0/1) for
+ * `segs` independent segments (offsets int64 [segs+1]), compute per segment loss = dot(relu?(err), lovasz_grad)
+ * and the per-position Lovasz gradient (lovasz.py:23-34,55-72,112-140).
+ *   relu != 0: hinge variant (relu on errors, lovasz.py:71); grad_sorted f32 [total] receives g_k (masked by
+ *   err>0 for hinge); seg_loss f32 [segs]. */
+TB_API int tb_lovasz_sorted(const float* err_sorted, const float* gt_sorted, const int64_t* seg_offsets_host, int segs,
+                     int relu, float* seg_loss, float* grad_sorted, void* ws, size_t ws_bytes, void* stream);
+TB_API size_t tb_lovasz_workspace_bytes(int64_t total, int segs);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bench helper: the deterministic, D4-non-equivariant stand-in "model" of SURVEY.md section 8(d):
+ *   y[b,k,i,j] = sum_c Wm[k,c]*x[b,c,i,j] + 0.01*(i - 2j + 7k)/T     (not part of the reference)
+ * ---------------------------------------------------------------------------------------------- */
+TB_API int tb_standin_model(const float* x, int B, int Cin, int K, int Th, int Tw, const float* Wm_host /*[K,Cin]*/,
+                     float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB200_H_ */

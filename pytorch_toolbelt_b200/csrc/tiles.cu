@@ -1,0 +1,1082 @@
+// Tile crop / TTA augment / TTA de-augment / weighted merge kernels for sm_100a.
+//
+// Everything here is HBM-bound index-permuting copy + a few flops per element, so the design rules are:
+// 128-bit coalesced global accesses on both sides, transposing D4 views staged through padded shared
+// memory, each byte of the big streams (augmented tiles out, model predictions in) touched exactly once,
+// grids of many small CTAs (several resident per SM) so that the memory system always has loads in flight.
+//
+// Reference semantics restated here (file:line relative to /root/reference/pytorch_toolbelt):
+//   inference/tiles.py:144-234  crop with border          -> crop_tiles_kernel, slice_augment_kernel
+//   inference/tta.py:257-484    *_image_augment           -> slice_augment_kernel, tta_augment_kernel
+//   inference/tta.py:287-524    *_image_deaugment         -> tta_deaugment_kernel, deaug_* helpers
+//   inference/tiles.py:310-350  TileMerger                -> deaugment_merge_kernel, normalize_crop_kernel
+//   (whole loop)                                          -> merge_all_kernel (output-stationary)
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <utility>
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kThreads = 256;
+constexpr int BS = 32;        // block edge (pixels) for 4- and 8-byte elements
+constexpr int PITCH = BS + 1; // shared-memory row pitch (elements): conflict-free transposed reads
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec4 {
+  T v[4];
+};
+
+__device__ __forceinline__ void ld_stream4(const float* p, float v[4]) {
+  const float4 q = __ldcs(reinterpret_cast<const float4*>(p));
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void ld_stream4(const double* p, double v[4]) {
+  const double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const double v[4]) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+
+__device__ __forceinline__ void st4(unsigned int* p, const unsigned int v[4]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(unsigned long long* p, const unsigned long long v[4]) {
+  reinterpret_cast<ulonglong2*>(p)[0] = make_ulonglong2(v[0], v[1]);
+  reinterpret_cast<ulonglong2*>(p)[1] = make_ulonglong2(v[2], v[3]);
+}
+__device__ __forceinline__ void st4(unsigned short* p, const unsigned short v[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) p[e] = v[e];
+}
+__device__ __forceinline__ void st4(unsigned char* p, const unsigned char v[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) p[e] = v[e];
+}
+
+// Vector float reduction into global memory (sm_90+): one RED.128 instead of four RED.32.
+__device__ __forceinline__ void red_add4(float* p, const float v[4]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void red_add1(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add1(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add4(double* p, const double v[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) atomicAdd(p + e, v[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. native-dtype HWC crop (ImageSlicer.split / iter_split / cut_patch on host arrays)
+// ------------------------------------------------------------------------------------------------
+struct CropArgs {
+  const void* img;
+  void* out;
+  const int32_t* xy;
+  int H, W, C, n, Th, Tw, border, clip_to_tile;
+  unsigned long long bval[4];
+};
+
+template <typename E>
+__global__ void __launch_bounds__(kThreads) crop_tiles_kernel(CropArgs a) {
+  const int t = blockIdx.y;
+  const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+  // valid ranges for the border remap
+  int ylo = 0, yhi = a.H, xlo = 0, xhi = a.W;
+  if (a.clip_to_tile) {
+    ylo = max(y0, 0); yhi = min(a.H, y0 + a.Th);
+    xlo = max(x0, 0); xhi = min(a.W, x0 + a.Tw);
+  }
+  const E* img = static_cast<const E*>(a.img);
+  E* out = static_cast<E*>(a.out) + (size_t)t * a.Th * a.Tw * a.C;
+  const int rowlen = a.Tw * a.C;
+  const long long total = (long long)a.Th * rowlen;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    const int i = (int)(idx / rowlen);
+    const int rem = (int)(idx - (long long)i * rowlen);
+    const int j = rem / a.C, c = rem - j * a.C;
+    const int sy = border_remap(y0 + i, ylo, yhi, a.border);
+    const int sx = border_remap(x0 + j, xlo, xhi, a.border);
+    E v;
+    if (sy < 0 || sx < 0) {
+      const unsigned long long bits = c < 4 ? a.bval[c] : 0ull;
+      v = (E)bits;
+    } else {
+      v = img[((size_t)sy * a.W + sx) * a.C + c];
+    }
+    out[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared "emit all views of one source block" routine (source-block-stationary augment).
+// sm holds the source block [BS][PITCH]; valid extents (vr, vc); block origin (R0, C0) inside a source
+// plane of (Hs, Ws). For every view a: out_a[i,j] = src[view_map(code_a, i, j, Hs, Ws)].
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__device__ __forceinline__ void emit_views(const T* sm, int R0, int C0, int vr, int vc, int Hs, int Ws,
+                                           ViewSet views, T* out_plane0, size_t view_stride) {
+  for (int a = 0; a < views.count; ++a) {
+    const unsigned code = view_code(views.packed, a);
+    const unsigned inv = view_inverse(code);
+    const int Ho = (code & V_T) ? Ws : Hs, Wo = (code & V_T) ? Hs : Ws;
+    // image of the source block under the inverse map: map both corners, take the min corner
+    int ia, ja, ib, jb;
+    view_map(inv, R0, C0, Ho, Wo, ia, ja);
+    view_map(inv, R0 + vr - 1, C0 + vc - 1, Ho, Wo, ib, jb);
+    const int oi0 = min(ia, ib), oj0 = min(ja, jb);
+    const int orows = (code & V_T) ? vc : vr, ocols = (code & V_T) ? vr : vc;
+    T* out = out_plane0 + (size_t)a * view_stride;
+    if (VEC) {
+      const int ngroups = ocols >> 2;
+      for (int idx = threadIdx.x; idx < orows * ngroups; idx += kThreads) {
+        const int li = idx / ngroups, lq = idx - li * ngroups;
+        const int i = oi0 + li, j = oj0 + 4 * lq;
+        T v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int si, sj;
+          view_map(code, i, j + e, Hs, Ws, si, sj);
+          v[e] = sm[(si - R0) * PITCH + (sj - C0)];
+        }
+        st4(out + (size_t)i * Wo + j, v);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < orows * ocols; idx += kThreads) {
+        const int li = idx / ocols, lj = idx - li * ocols;
+        const int i = oi0 + li, j = oj0 + lj;
+        int si, sj;
+        view_map(code, i, j, Hs, Ws, si, sj);
+        out[(size_t)i * Wo + j] = sm[(si - R0) * PITCH + (sj - C0)];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. slice + HWC->CHW + cast + TTA augment
+// ------------------------------------------------------------------------------------------------
+struct SliceArgs {
+  const void* img;
+  float* out;
+  const int32_t* xy;
+  int layout, H, W, C, n, Th, Tw, border;
+  int nbx, nby;  // blocks per tile
+  ViewSet views;
+  float bval[4];
+  int has_affine;
+  float scale[8], bias[8];  // first 8 channels by value; more channels -> identity (host rejects)
+};
+
+__device__ __forceinline__ float to_f32(unsigned char v) { return (float)v; }
+__device__ __forceinline__ float to_f32(unsigned short v) { return (float)v; }
+__device__ __forceinline__ float to_f32(short v) { return (float)v; }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+template <typename SrcT, bool VEC>
+__global__ void __launch_bounds__(kThreads) slice_augment_kernel(SliceArgs a) {
+  __shared__ float sm[BS * PITCH];
+  const int per_tile = a.nbx * a.nby;
+  const int t = blockIdx.x / per_tile;
+  const int blk = blockIdx.x - t * per_tile;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int R0 = by * BS, C0 = bx * BS;
+  const int vr = min(BS, a.Th - R0), vc = min(BS, a.Tw - C0);
+  const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+  const SrcT* img = static_cast<const SrcT*>(a.img);
+  const size_t plane = (size_t)a.Th * a.Tw;
+  const size_t view_stride = (size_t)a.n * a.C * plane;
+
+  for (int c = 0; c < a.C; ++c) {
+    // ---- load the source block of channel c (coalesced along x; border synthesised) ----
+    for (int idx = threadIdx.x; idx < vr * vc; idx += kThreads) {
+      const int lr = idx / vc, lc = idx - lr * vc;
+      const int sy = border_remap(y0 + R0 + lr, 0, a.H, a.border);
+      const int sx = border_remap(x0 + C0 + lc, 0, a.W, a.border);
+      float v;
+      if (sy < 0 || sx < 0) {
+        v = c < 4 ? a.bval[c] : 0.f;
+      } else if (a.layout == TB_HWC) {
+        v = to_f32(img[((size_t)sy * a.W + sx) * a.C + c]);
+      } else {
+        v = to_f32(img[((size_t)c * a.H + sy) * a.W + sx]);
+      }
+      if (a.has_affine && c < 8) v = __fadd_rn(__fmul_rn(v, a.scale[c]), a.bias[c]);
+      sm[lr * PITCH + lc] = v;
+    }
+    __syncthreads();
+    emit_views<float, VEC>(sm, R0, C0, vr, vc, a.Th, a.Tw, a.views, a.out + ((size_t)t * a.C + c) * plane,
+                           view_stride);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. stand-alone TTA augment on [B,C,H,W] (any element width)
+// ------------------------------------------------------------------------------------------------
+struct AugArgs {
+  const void* x;
+  void* out;
+  int planes;  // B*C
+  int H, W, nbx, nby;
+  ViewSet views;
+  size_t view_stride;  // B*C*H*W elements
+};
+
+template <typename E, bool VEC>
+__global__ void __launch_bounds__(kThreads) tta_augment_kernel(AugArgs a) {
+  __shared__ E sm[BS * PITCH];
+  const int per_plane = a.nbx * a.nby;
+  const int p = blockIdx.x / per_plane;
+  const int blk = blockIdx.x - p * per_plane;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int R0 = by * BS, C0 = bx * BS;
+  const int vr = min(BS, a.H - R0), vc = min(BS, a.W - C0);
+  const E* src = static_cast<const E*>(a.x) + (size_t)p * a.H * a.W;
+  for (int idx = threadIdx.x; idx < vr * vc; idx += kThreads) {
+    const int lr = idx / vc, lc = idx - lr * vc;
+    sm[lr * PITCH + lc] = src[(size_t)(R0 + lr) * a.W + C0 + lc];
+  }
+  __syncthreads();
+  emit_views<E, VEC>(sm, R0, C0, vr, vc, a.H, a.W, a.views, static_cast<E*>(a.out) + (size_t)p * a.H * a.W,
+                     a.view_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// De-augment gather machinery (output-block-stationary).
+//
+// The calling CTA owns the output block rows [i0,i0+BS) x cols [j0,j0+BS) of a de-augmented plane of
+// (Ho, Wo); thread (li, lq) = (tid/8, tid%8) owns pixels (i0+li, j0+4*lq+e), e = 0..3.
+// For view a the value is  src_a[view_map(g_a, i, j, Hs, Ws)]  with g_a = inverse of the augment code.
+// Non-transposing views are read straight from global memory (row-contiguous, possibly reversed);
+// transposing views are staged through shared memory (coalesced row reads, conflict-free column reads).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void gather_direct4(const T* __restrict__ plane, unsigned g, int i, int j, int Hs,
+                                               int Ws, T v[4]) {
+  // caller guarantees 0 <= i < Ho (= Hs for non-transposing views); pixels with j+e outside [0,Ws) give 0
+  const int si = (g & V_FI) ? Hs - 1 - i : i;
+  const T* row = plane + (size_t)si * Ws;
+  const bool rev = (g & V_FJ) != 0;
+  const int sj0 = rev ? Ws - 4 - j : j;  // first (lowest) source column of the 4-group
+  if (ALIGNED && sj0 >= 0 && sj0 + 3 < Ws) {
+    T q[4];
+    ld_stream4(row + sj0, q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = rev ? q[3 - e] : q[e];
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int sj = rev ? Ws - 1 - (j + e) : j + e;
+      v[e] = (j + e >= 0 && sj >= 0 && sj < Ws) ? __ldcs(row + sj) : T(0);
+    }
+  }
+}
+
+// Stage the source block a transposing view needs for output block (i0, j0) into sm[BS][PITCH].
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void stage_transposed(const T* __restrict__ plane, unsigned g, int i0, int j0, int Hs,
+                                                 int Ws, T* sm, int& sr0, int& sc0) {
+  // (a,b) = (j,i): source row depends on j, source column on i
+  sr0 = (g & V_FI) ? Hs - j0 - BS : j0;
+  sc0 = (g & V_FJ) ? Ws - i0 - BS : i0;
+  const int lr = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int sr = sr0 + lr, sc = sc0 + 4 * lq;
+  T q[4] = {T(0), T(0), T(0), T(0)};
+  if (sr >= 0 && sr < Hs) {
+    const T* row = plane + (size_t)sr * Ws;
+    if (ALIGNED && sc >= 0 && sc + 3 < Ws) {
+      ld_stream4(row + sc, q);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (sc + e >= 0 && sc + e < Ws) q[e] = __ldcs(row + sc + e);
+    }
+  }
+  T* dst = sm + lr * PITCH + 4 * lq;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) dst[e] = q[e];
+}
+
+template <typename T>
+__device__ __forceinline__ void read_transposed4(const T* sm, unsigned g, int i, int j, int Hs, int Ws, int sr0,
+                                                 int sc0, T v[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int si, sj;
+    view_map(g, i, j + e, Hs, Ws, si, sj);
+    const int rr = si - sr0, cc = sj - sc0;
+    v[e] = (rr >= 0 && rr < BS && cc >= 0 && cc < BS) ? sm[rr * PITCH + cc] : T(0);
+  }
+}
+
+__host__ __device__ constexpr bool packed_has_transpose(unsigned packed, int count) {
+  for (int a = 0; a < count; ++a)
+    if ((packed >> (3 * a)) & V_T) return true;
+  return false;
+}
+__host__ __device__ inline bool views_have_transpose(ViewSet v) { return packed_has_transpose(v.packed, v.count); }
+
+// Compile-time view sets (same tables as make_views) so that the per-view loops unroll with static
+// register indexing.
+template <int TTA>
+struct Views;
+#define TB_VIEWS(TTA, COUNT, ...)                                     \
+  template <>                                                         \
+  struct Views<TTA> {                                                 \
+    static constexpr int count = COUNT;                               \
+    static constexpr unsigned packed = pack_views({__VA_ARGS__});     \
+  };
+constexpr unsigned pack_views(std::initializer_list<unsigned> codes) {
+  unsigned p = 0;
+  int a = 0;
+  for (unsigned c : codes) p |= c << (3 * a++);
+  return p;
+}
+TB_VIEWS(TB_TTA_NONE, 1, V_ID)
+TB_VIEWS(TB_TTA_FLIPLR, 2, V_ID, V_FJ)
+TB_VIEWS(TB_TTA_FLIPUD, 2, V_ID, V_FI)
+TB_VIEWS(TB_TTA_FLIPS, 3, V_ID, V_FJ, V_FI)
+TB_VIEWS(TB_TTA_D2, 4, V_ID, V_FJ, V_FI, V_FI | V_FJ)
+TB_VIEWS(TB_TTA_D4, 8, V_ID, V_T | V_FI, V_FI | V_FJ, V_T | V_FJ, V_T, V_FJ, V_T | V_FI | V_FJ, V_FI)
+#undef TB_VIEWS
+
+// De-augment + reduce the 4 pixels of the calling thread for one (tile/batch item, channel) plane set.
+//   plane0       pointer to view 0's plane; view a is plane0 + a*view_stride
+//   (Hs, Ws)     plane dims (identical for all views: transposing views require square planes)
+//   sm           CTA-shared staging: [nT][BS][PITCH], nT = number of transposing views (<= 4)
+// Contains two __syncthreads() when the view set has transposing views: call it from uniform control flow.
+template <typename T, bool ALIGNED, unsigned PACKED, int COUNT>
+__device__ __forceinline__ void deaug_reduce4(const T* __restrict__ plane0, size_t view_stride, int red, int i0,
+                                              int j0, int Hs, int Ws, T* sm, T out[4]) {
+  constexpr bool HAS_T = packed_has_transpose(PACKED, COUNT);
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int i = i0 + li, j = j0 + 4 * lq;
+  const bool row_ok = (i >= 0 && i < Hs);
+  int sr0[4], sc0[4];
+  if (HAS_T) {
+    int slot = 0;
+#pragma unroll
+    for (int a = 0; a < COUNT; ++a) {
+      const unsigned g = view_inverse((PACKED >> (3 * a)) & 7u);
+      if (g & V_T) {
+        stage_transposed<T, ALIGNED>(plane0 + (size_t)a * view_stride, g, i0, j0, Hs, Ws, sm + slot * BS * PITCH,
+                                     sr0[slot], sc0[slot]);
+        ++slot;
+      }
+    }
+  }
+  // issue the direct loads before the barrier so they overlap the staging traffic
+  T direct[4][4];
+  {
+    int d = 0;
+#pragma unroll
+    for (int a = 0; a < COUNT; ++a) {
+      const unsigned g = view_inverse((PACKED >> (3 * a)) & 7u);
+      if (!(g & V_T)) {
+        if (row_ok)
+          gather_direct4<T, ALIGNED>(plane0 + (size_t)a * view_stride, g, i, j, Hs, Ws, direct[d]);
+        else
+          direct[d][0] = direct[d][1] = direct[d][2] = direct[d][3] = T(0);
+        ++d;
+      }
+    }
+  }
+  if (HAS_T) __syncthreads();
+  T acc[4] = {T(0), T(0), T(0), T(0)};
+  {
+    int d = 0, slot = 0;
+#pragma unroll
+    for (int a = 0; a < COUNT; ++a) {
+      const unsigned g = view_inverse((PACKED >> (3 * a)) & 7u);
+      T v[4];
+      if (g & V_T) {
+        read_transposed4<T>(sm + slot * BS * PITCH, g, i, j, Hs, Ws, sr0[slot], sc0[slot], v);
+        ++slot;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = direct[d][e];
+        ++d;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const T pv = red_pre<T>(red, v[e]);
+        acc[e] = (a == 0) ? pv : add_rn(acc[e], pv);  // sequential view-order sum (torch CPU mean/sum)
+      }
+    }
+  }
+  if (HAS_T) __syncthreads();  // staging buffer may be overwritten by the caller's next plane
+#pragma unroll
+  for (int e = 0; e < 4; ++e) out[e] = red_post<T>(red, acc[e], COUNT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. stand-alone TTA de-augment (+ reduction)
+// ------------------------------------------------------------------------------------------------
+struct DeaugArgs {
+  const void* x;
+  void* out;
+  int planes;  // B*C
+  int H, W, nbx, nby, red;
+  ViewSet views;
+  size_t view_stride;
+};
+
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void store_out4(T* o, int i, int j, int H, int W, const T v[4]) {
+  if (i < H) {
+    if (ALIGNED && j + 3 < W) {
+      st4(o, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (j + e < W) o[e] = v[e];
+    }
+  }
+}
+
+template <typename T, bool ALIGNED, unsigned PACKED, int... Is>
+__device__ __forceinline__ void deaug_keep_views(const DeaugArgs& a, const T* plane0, int p, int i0, int j0, T* sm,
+                                                 std::integer_sequence<int, Is...>) {
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int i = i0 + li, j = j0 + 4 * lq;
+  // one view at a time through the same machinery (a 1-view "sum" is the inverse-permuted copy)
+  (
+      [&] {
+        T v[4];
+        deaug_reduce4<T, ALIGNED, (PACKED >> (3 * Is)) & 7u, 1>(plane0 + (size_t)Is * a.view_stride, 0, TB_RED_SUM, i0,
+                                                               j0, a.H, a.W, sm, v);
+        T* o = static_cast<T*>(a.out) + (size_t)Is * a.view_stride + (size_t)p * a.H * a.W + (size_t)i * a.W + j;
+        store_out4<T, ALIGNED>(o, i, j, a.H, a.W, v);
+      }(),
+      ...);
+}
+
+template <typename T, bool ALIGNED, int TTA>
+__global__ void __launch_bounds__(kThreads) tta_deaugment_kernel(DeaugArgs a) {
+  using V = Views<TTA>;
+  __shared__ T sm[(packed_has_transpose(V::packed, V::count) ? 4 : 1) * BS * PITCH];
+  const int per_plane = a.nbx * a.nby;
+  const int p = blockIdx.x / per_plane;
+  const int blk = blockIdx.x - p * per_plane;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int i0 = by * BS, j0 = bx * BS;
+  const T* plane0 = static_cast<const T*>(a.x) + (size_t)p * a.H * a.W;
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int i = i0 + li, j = j0 + 4 * lq;
+  if (a.red != TB_RED_NONE) {
+    T v[4];
+    deaug_reduce4<T, ALIGNED, V::packed, V::count>(plane0, a.view_stride, a.red, i0, j0, a.H, a.W, sm, v);
+    T* o = static_cast<T*>(a.out) + (size_t)p * a.H * a.W + (size_t)i * a.W + j;
+    store_out4<T, ALIGNED>(o, i, j, a.H, a.W, v);
+  } else {
+    deaug_keep_views<T, ALIGNED, V::packed>(a, plane0, p, i0, j0, sm, std::make_integer_sequence<int, V::count>{});
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. streaming scatter merge with fused de-augment (TileMerger.integrate_batch [+ *_image_deaugment])
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct MergeArgs {
+  const T* pred;  // [A*n,K,Th,Tw]
+  T* image;       // [K,Hp,Wp]
+  T* norm;        // [Hp,Wp] or null
+  TileXY xy;
+  int n, K, Th, Tw, Hp, Wp, nbx, nby, red;
+  ViewSet views;
+  WeightDev<T> w;
+};
+
+template <typename T, bool ALIGNED, int TTA>
+__global__ void __launch_bounds__(kThreads) deaugment_merge_kernel(MergeArgs<T> a) {
+  using V = Views<TTA>;
+  __shared__ T sm[(packed_has_transpose(V::packed, V::count) ? 4 : 1) * BS * PITCH];
+  const int per_tile = a.nbx * a.nby;
+  const int t = blockIdx.x / per_tile;
+  const int blk = blockIdx.x - t * per_tile;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int i0 = by * BS, j0 = bx * BS;
+  int x0, y0;
+  a.xy.get(t, x0, y0);
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int i = i0 + li, j = j0 + 4 * lq;
+  const size_t plane = (size_t)a.Th * a.Tw;
+  const size_t view_stride = (size_t)a.n * a.K * plane;
+  const bool row_ok = i < a.Th;
+  // weights of this thread's 4 pixels
+  T w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) w[e] = (row_ok && j + e < a.Tw) ? weight_at<T>(a.w, i, j + e) : T(0);
+  const size_t cpix = (size_t)(y0 + i) * a.Wp + (x0 + j);
+  // vector reductions need a 16-byte aligned canvas address
+  const bool vec_ok = ALIGNED && ((x0 & 3) == 0) && ((a.Wp & 3) == 0) && (j + 3 < a.Tw);
+  for (int k = 0; k < a.K; ++k) {
+    T v[4];
+    deaug_reduce4<T, ALIGNED, V::packed, V::count>(a.pred + ((size_t)t * a.K + k) * plane, view_stride, a.red, i0,
+                                                   j0, a.Th, a.Tw, sm, v);
+    if (row_ok) {
+      T* dst = a.image + (size_t)k * a.Hp * a.Wp + cpix;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = mul_rn(v[e], w[e]);
+      if (vec_ok) {
+        red_add4(dst, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e < a.Tw) red_add1(dst + e, v[e]);
+      }
+    }
+  }
+  if (a.norm && row_ok) {
+    T* dst = a.norm + cpix;
+    if (vec_ok) {
+      red_add4(dst, w);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (j + e < a.Tw) red_add1(dst + e, w[e]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 6. normalise + crop
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) normalize_crop_kernel(const T* __restrict__ image,
+                                                                  const T* __restrict__ norm, int K, int Hp, int Wp,
+                                                                  int top, int left, int H, int W, T eps, int use_eps,
+                                                                  T* out) {
+  const long long total = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
+    const size_t src = (size_t)(top + i) * Wp + (left + j);
+    T d = norm[src];
+    if (use_eps) d = max(d, eps);
+    for (int k = 0; k < K; ++k) out[(size_t)k * total + idx] = image[(size_t)k * Hp * Wp + src] / d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 7. output-stationary fused de-augment + merge + normalise + crop
+// ------------------------------------------------------------------------------------------------
+struct MergeAllArgs {
+  const float* pred;
+  tb_grid grid;
+  int K, red, Hp, Wp, y0, y1, r0, r1, raw, top, left, H, W;
+  int bx0, nbx, nby;  // block-column offset and block counts covering the requested window
+  ViewSet views;
+  WeightDev<float> w;
+  const float* init_num;
+  const float* init_den;
+  float* out_num;
+  float* out_den;
+};
+
+template <bool ALIGNED, int TTA>
+__global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
+  using V = Views<TTA>;
+  __shared__ float sm[(packed_has_transpose(V::packed, V::count) ? 4 : 1) * BS * PITCH];
+  const tb_grid& g = a.grid;
+  const int by = blockIdx.x / a.nbx, bxi = blockIdx.x - by * a.nbx;
+  const int Y0 = a.y0 - (a.y0 % BS) + by * BS;  // blocks are aligned to the canvas origin
+  const int X0 = (a.bx0 + bxi) * BS;
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int y = Y0 + li, x = X0 + 4 * lq;
+  const size_t plane = (size_t)g.Th * g.Tw;
+  const size_t view_stride = (size_t)g.n_slots * a.K * plane;
+  const int rows = a.y1 - a.y0;
+
+  // covering tile rows / columns of this block (any pixel of the block)
+  int ra = (Y0 - g.Th + g.Sy) / g.Sy;  // ceil((Y0 - Th + 1)/Sy) for non-negative numerators
+  if (Y0 - g.Th + 1 <= 0) ra = 0;
+  int rb = (Y0 + BS - 1) / g.Sy;
+  ra = max(ra, a.r0);
+  rb = min(rb, min(g.ny, a.r1) - 1);
+  int ca = (X0 - g.Tw + g.Sx) / g.Sx;
+  if (X0 - g.Tw + 1 <= 0) ca = 0;
+  int cb = min((X0 + BS - 1) / g.Sx, g.nx - 1);
+
+  const bool y_ok = (y >= a.y0 && y < a.y1);
+  for (int k = 0; k < a.K; ++k) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.init_num && y_ok) {
+      const size_t o = (size_t)(y - a.y0) * a.Wp + x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (x + e < a.Wp) {
+          acc[e] = a.init_num[(size_t)k * rows * a.Wp + o + e];
+          den[e] = a.init_den[o + e];
+        }
+    }
+    for (int r = ra; r <= rb; ++r) {
+      for (int c = ca; c <= cb; ++c) {
+        const int t = r * g.nx + c;
+        const float* base;
+        size_t vstride = view_stride;
+        if (g.tile_ptr) {
+          base = g.tile_ptr[t];
+          if (!base) continue;  // uniform across the CTA
+          vstride = (size_t)__ldg(g.tile_vstride + t);
+        } else {
+          const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+          if (slot < 0) continue;  // uniform across the CTA
+          base = a.pred + (size_t)slot * a.K * plane;
+        }
+        const int i0 = Y0 - r * g.Sy, j0 = X0 - c * g.Sx;
+        float v[4];
+        deaug_reduce4<float, ALIGNED, V::packed, V::count>(base + (size_t)k * plane, vstride, a.red, i0, j0, g.Th,
+                                                           g.Tw, sm, v);
+        const int i = i0 + li, j = j0 + 4 * lq;
+        if (i >= 0 && i < g.Th) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (j + e >= 0 && j + e < g.Tw) {
+              const float w = weight_at<float>(a.w, i, j + e);
+              acc[e] = add_rn(acc[e], mul_rn(v[e], w));
+              den[e] = add_rn(den[e], w);
+            }
+          }
+        }
+      }
+    }
+    if (!y_ok) continue;
+    if (a.raw) {
+      const size_t o = (size_t)(y - a.y0) * a.Wp + x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (x + e < a.Wp) {
+          a.out_num[(size_t)k * rows * a.Wp + o + e] = acc[e];
+          if (k == 0) a.out_den[o + e] = den[e];
+        }
+    } else {
+      const int oi = y - a.top;
+      if (oi >= 0 && oi < a.H) {
+        float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
+        const int oj = x - a.left;
+        if (ALIGNED && ((a.left & 3) == 0) && ((a.W & 3) == 0) && oj >= 0 && oj + 3 < a.W) {
+          float q[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q[e] = acc[e] / den[e];
+          __stcs(reinterpret_cast<float4*>(o + oj), make_float4(q[0], q[1], q[2], q[3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (oj + e >= 0 && oj + e < a.W) o[oj + e] = acc[e] / den[e];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 8. stand-in model (bench / tests only): y[b,k,i,j] = sum_c Wm[k,c] x[b,c,i,j] + 0.01 (i - 2j + 7k)/T
+// ------------------------------------------------------------------------------------------------
+struct StandinArgs {
+  const float* x;
+  float* y;
+  int B, Cin, K, Th, Tw;
+  float Wm[64];
+};
+
+__global__ void __launch_bounds__(kThreads) standin_model_kernel(StandinArgs a) {
+  const size_t plane = (size_t)a.Th * a.Tw;
+  const size_t quads = plane / 4;
+  const size_t total = (size_t)a.B * quads;
+  for (size_t idx = (size_t)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (size_t)gridDim.x * kThreads) {
+    const size_t b = idx / quads, q = idx - b * quads;
+    const int i = (int)((q * 4) / a.Tw), j = (int)((q * 4) - (size_t)i * a.Tw);
+    float4 xin[8];
+    for (int c = 0; c < a.Cin; ++c) xin[c] = __ldcs(reinterpret_cast<const float4*>(a.x + (b * a.Cin + c) * plane) + q);
+    for (int k = 0; k < a.K; ++k) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = 0.01f * (float)(i - 2 * (j + e) + 7 * k) / (float)a.Th;
+      for (int c = 0; c < a.Cin; ++c) {
+        const float wkc = a.Wm[k * a.Cin + c];
+        o[0] = fmaf(wkc, xin[c].x, o[0]);
+        o[1] = fmaf(wkc, xin[c].y, o[1]);
+        o[2] = fmaf(wkc, xin[c].z, o[2]);
+        o[3] = fmaf(wkc, xin[c].w, o[3]);
+      }
+      __stcs(reinterpret_cast<float4*>(a.y + (b * a.K + k) * plane) + q, make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace tb
+
+using namespace tb;
+
+// Run `BODY` with TTA_ bound to the compile-time TTA group.
+#define TB_DISPATCH_TTA(tta, ...)                                        \
+  switch (tta) {                                                         \
+    case TB_TTA_NONE: { constexpr int TTA_ = TB_TTA_NONE; __VA_ARGS__; break; }     \
+    case TB_TTA_FLIPLR: { constexpr int TTA_ = TB_TTA_FLIPLR; __VA_ARGS__; break; } \
+    case TB_TTA_FLIPUD: { constexpr int TTA_ = TB_TTA_FLIPUD; __VA_ARGS__; break; } \
+    case TB_TTA_FLIPS: { constexpr int TTA_ = TB_TTA_FLIPS; __VA_ARGS__; break; }   \
+    case TB_TTA_D2: { constexpr int TTA_ = TB_TTA_D2; __VA_ARGS__; break; }         \
+    case TB_TTA_D4: { constexpr int TTA_ = TB_TTA_D4; __VA_ARGS__; break; }         \
+    default: break;                                                      \
+  }
+
+// ================================================================================================
+// C-ABI entry points
+// ================================================================================================
+extern "C" {
+
+int tb_tta_views(int tta) {
+  ViewSet v;
+  if (!make_views(tta, &v)) return fail(TB_ERR_ARG, "tb_tta_views: unknown tta %d", tta);
+  return v.count;
+}
+
+int tb_crop_tiles(const void* img, int elem_bytes, int H, int W, int C, const int32_t* xy, int n, int Th, int Tw,
+                  int border_type, const uint64_t* border_value_host, int clip_to_tile, void* out, void* stream) {
+  TB_REQUIRE(img && xy && out, TB_ERR_ARG, "tb_crop_tiles: null pointer");
+  TB_REQUIRE(H > 0 && W > 0 && C > 0 && Th > 0 && Tw > 0 && n >= 0, TB_ERR_ARG, "tb_crop_tiles: bad shape");
+  TB_REQUIRE(border_type >= 0 && border_type <= 4, TB_ERR_ARG, "tb_crop_tiles: bad border_type %d", border_type);
+  TB_REQUIRE(n <= 65535, TB_ERR_ARG, "tb_crop_tiles: n > 65535");
+  if (n == 0) return TB_OK;
+  CropArgs a;
+  a.img = img; a.out = out; a.xy = xy;
+  a.H = H; a.W = W; a.C = C; a.n = n; a.Th = Th; a.Tw = Tw; a.border = border_type; a.clip_to_tile = clip_to_tile;
+  for (int c = 0; c < 4; ++c) a.bval[c] = border_value_host ? border_value_host[c] : 0ull;
+  const long long total = (long long)Th * Tw * C;
+  const int gx = (int)std::min<long long>((total + kThreads - 1) / kThreads, 4096);
+  dim3 grid(gx, n);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (elem_bytes) {
+    case 1: crop_tiles_kernel<unsigned char><<<grid, kThreads, 0, s>>>(a); break;
+    case 2: crop_tiles_kernel<unsigned short><<<grid, kThreads, 0, s>>>(a); break;
+    case 4: crop_tiles_kernel<unsigned int><<<grid, kThreads, 0, s>>>(a); break;
+    case 8: crop_tiles_kernel<unsigned long long><<<grid, kThreads, 0, s>>>(a); break;
+    default: return fail(TB_ERR_ARG, "tb_crop_tiles: elem_bytes must be 1, 2, 4 or 8 (got %d)", elem_bytes);
+  }
+  TB_LAUNCH_CHECK("crop_tiles_kernel");
+  return TB_OK;
+}
+
+int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, int C, const int32_t* xy, int n,
+                     int Th, int Tw, int tta, int border_type, const float* border_value_host,
+                     const float* scale_host, const float* bias_host, float* out, void* stream) {
+  TB_REQUIRE(img && xy && out, TB_ERR_ARG, "tb_slice_augment: null pointer");
+  TB_REQUIRE(H > 0 && W > 0 && C > 0 && Th > 0 && Tw > 0 && n >= 0, TB_ERR_ARG, "tb_slice_augment: bad shape");
+  TB_REQUIRE(layout == TB_HWC || layout == TB_CHW, TB_ERR_ARG, "tb_slice_augment: bad layout %d", layout);
+  TB_REQUIRE(border_type >= 0 && border_type <= 4, TB_ERR_ARG, "tb_slice_augment: bad border_type %d", border_type);
+  SliceArgs a;
+  TB_REQUIRE(make_views(tta, &a.views), TB_ERR_ARG, "tb_slice_augment: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(a.views) || Th == Tw, TB_ERR_ARG,
+             "tb_slice_augment: D4 needs square tiles (got %dx%d)", Th, Tw);
+  TB_REQUIRE(!(scale_host || bias_host) || C <= 8, TB_ERR_UNSUPPORTED,
+             "tb_slice_augment: per-channel affine supports C <= 8");
+  if (n == 0) return TB_OK;
+  a.img = img; a.out = out; a.xy = xy; a.layout = layout;
+  a.H = H; a.W = W; a.C = C; a.n = n; a.Th = Th; a.Tw = Tw; a.border = border_type;
+  a.nbx = (Tw + BS - 1) / BS; a.nby = (Th + BS - 1) / BS;
+  for (int c = 0; c < 4; ++c) a.bval[c] = border_value_host ? border_value_host[c] : 0.f;
+  a.has_affine = (scale_host || bias_host) ? 1 : 0;
+  for (int c = 0; c < 8; ++c) {
+    a.scale[c] = (scale_host && c < C) ? scale_host[c] : 1.f;
+    a.bias[c] = (bias_host && c < C) ? bias_host[c] : 0.f;
+  }
+  const long long blocks = (long long)n * a.nbx * a.nby;
+  TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_slice_augment: grid too large");
+  const bool vec = (Th % 4 == 0) && (Tw % 4 == 0) && aligned16(out);
+  cudaStream_t s = (cudaStream_t)stream;
+#define TB_SLICE(SrcT)                                                                   \
+  do {                                                                                   \
+    if (vec)                                                                             \
+      slice_augment_kernel<SrcT, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);         \
+    else                                                                                 \
+      slice_augment_kernel<SrcT, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);        \
+  } while (0)
+  switch (img_dtype) {
+    case TB_U8: TB_SLICE(unsigned char); break;
+    case TB_U16: TB_SLICE(unsigned short); break;
+    case TB_I16: TB_SLICE(short); break;
+    case TB_F16: TB_SLICE(__half); break;
+    case TB_F32: TB_SLICE(float); break;
+    default: return fail(TB_ERR_UNSUPPORTED, "tb_slice_augment: unsupported image dtype %d", img_dtype);
+  }
+#undef TB_SLICE
+  TB_LAUNCH_CHECK("slice_augment_kernel");
+  return TB_OK;
+}
+
+int tb_tta_augment(const void* x, int elem_bytes, int B, int C, int H, int W, int tta, void* out, void* stream) {
+  TB_REQUIRE(x && out, TB_ERR_ARG, "tb_tta_augment: null pointer");
+  TB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, TB_ERR_ARG, "tb_tta_augment: bad shape");
+  AugArgs a;
+  TB_REQUIRE(make_views(tta, &a.views), TB_ERR_ARG, "tb_tta_augment: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(a.views) || H == W, TB_ERR_ARG, "tb_tta_augment: D4 needs square input (%dx%d)",
+             H, W);
+  if (B == 0) return TB_OK;
+  a.x = x; a.out = out; a.planes = B * C; a.H = H; a.W = W;
+  a.nbx = (W + BS - 1) / BS; a.nby = (H + BS - 1) / BS;
+  a.view_stride = (size_t)B * C * H * W;
+  const long long blocks = (long long)a.planes * a.nbx * a.nby;
+  TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_tta_augment: grid too large");
+  const bool vec = (H % 4 == 0) && (W % 4 == 0) && aligned16(out);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (elem_bytes) {
+    case 1: tta_augment_kernel<unsigned char, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
+    case 2: tta_augment_kernel<unsigned short, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
+    case 4:
+      if (vec)
+        tta_augment_kernel<unsigned int, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      else
+        tta_augment_kernel<unsigned int, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      break;
+    case 8:
+      if (vec)
+        tta_augment_kernel<unsigned long long, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      else
+        tta_augment_kernel<unsigned long long, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      break;
+    default: return fail(TB_ERR_ARG, "tb_tta_augment: elem_bytes must be 1, 2, 4 or 8 (got %d)", elem_bytes);
+  }
+  TB_LAUNCH_CHECK("tta_augment_kernel");
+  return TB_OK;
+}
+
+int tb_view_permute(const void* x, int elem_bytes, int planes, int H, int W, int view_code, void* out, void* stream) {
+  TB_REQUIRE(x && out, TB_ERR_ARG, "tb_view_permute: null pointer");
+  TB_REQUIRE(planes >= 0 && H > 0 && W > 0, TB_ERR_ARG, "tb_view_permute: bad shape");
+  TB_REQUIRE(view_code >= 0 && view_code < 8, TB_ERR_ARG, "tb_view_permute: view_code must be in [0,8)");
+  if (planes == 0) return TB_OK;
+  AugArgs a;
+  a.views.count = 1;
+  a.views.packed = (unsigned)view_code;
+  a.x = x; a.out = out; a.planes = planes; a.H = H; a.W = W;
+  a.nbx = (W + BS - 1) / BS; a.nby = (H + BS - 1) / BS;
+  a.view_stride = 0;
+  const long long blocks = (long long)planes * a.nbx * a.nby;
+  TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_view_permute: grid too large");
+  const bool vec = (H % 4 == 0) && (W % 4 == 0) && aligned16(out);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (elem_bytes) {
+    case 1: tta_augment_kernel<unsigned char, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
+    case 2: tta_augment_kernel<unsigned short, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
+    case 4:
+      if (vec)
+        tta_augment_kernel<unsigned int, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      else
+        tta_augment_kernel<unsigned int, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      break;
+    case 8:
+      if (vec)
+        tta_augment_kernel<unsigned long long, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      else
+        tta_augment_kernel<unsigned long long, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+      break;
+    default: return fail(TB_ERR_ARG, "tb_view_permute: elem_bytes must be 1, 2, 4 or 8 (got %d)", elem_bytes);
+  }
+  TB_LAUNCH_CHECK("tta_augment_kernel(view_permute)");
+  return TB_OK;
+}
+
+int tb_tta_deaugment(const void* x, int dtype, int B, int C, int H, int W, int tta, int reduction, void* out,
+                     void* stream) {
+  TB_REQUIRE(x && out, TB_ERR_ARG, "tb_tta_deaugment: null pointer");
+  TB_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, TB_ERR_ARG, "tb_tta_deaugment: bad shape");
+  TB_REQUIRE(reduction >= TB_RED_NONE && reduction <= TB_RED_LOG1P, TB_ERR_ARG, "tb_tta_deaugment: bad reduction %d",
+             reduction);
+  DeaugArgs a;
+  TB_REQUIRE(make_views(tta, &a.views), TB_ERR_ARG, "tb_tta_deaugment: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(a.views) || H == W, TB_ERR_ARG, "tb_tta_deaugment: D4 needs square input (%dx%d)",
+             H, W);
+  if (B == 0) return TB_OK;
+  a.x = x; a.out = out; a.planes = B * C; a.H = H; a.W = W; a.red = reduction;
+  a.nbx = (W + BS - 1) / BS; a.nby = (H + BS - 1) / BS;
+  a.view_stride = (size_t)B * C * H * W;
+  const long long blocks = (long long)a.planes * a.nbx * a.nby;
+  TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_tta_deaugment: grid too large");
+  const bool al = (H % 4 == 0) && (W % 4 == 0) && aligned16(x) && aligned16(out);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == TB_F32) {
+    if (al) {
+      TB_DISPATCH_TTA(tta, tta_deaugment_kernel<float, true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+    } else {
+      TB_DISPATCH_TTA(tta, tta_deaugment_kernel<float, false, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+    }
+  } else if (dtype == TB_F64) {
+    if (al) {
+      TB_DISPATCH_TTA(tta, tta_deaugment_kernel<double, true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+    } else {
+      TB_DISPATCH_TTA(tta, tta_deaugment_kernel<double, false, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+    }
+  } else {
+    return fail(TB_ERR_UNSUPPORTED, "tb_tta_deaugment: dtype must be TB_F32 or TB_F64 (got %d)", dtype);
+  }
+  TB_LAUNCH_CHECK("tta_deaugment_kernel");
+  return TB_OK;
+}
+
+}  // extern "C"
+
+template <typename T>
+static int launch_deaugment_merge(const void* pred, const int32_t* xy, int xy_is_host, int n, int K, int Th, int Tw,
+                                  int tta, ViewSet views, int reduction, const tb_weight* weight, void* image, void* norm,
+                                  int Hp, int Wp, cudaStream_t s) {
+  MergeArgs<T> a;
+  a.pred = (const T*)pred; a.image = (T*)image; a.norm = (T*)norm;
+  a.n = n; a.K = K; a.Th = Th; a.Tw = Tw; a.Hp = Hp; a.Wp = Wp; a.red = reduction; a.views = views;
+  a.nbx = (Tw + BS - 1) / BS; a.nby = (Th + BS - 1) / BS;
+  if (!make_weight<T>(weight, Th, Tw, &a.w)) return fail(TB_ERR_ARG, "tb_deaugment_merge: bad weight spec");
+  if (xy_is_host) {
+    if (n > kMaxInlineTiles)
+      return fail(TB_ERR_ARG, "tb_deaugment_merge: host coordinates allow n <= %d (got %d)", kMaxInlineTiles, n);
+    a.xy.dev = nullptr;
+    for (int t = 0; t < n; ++t) {
+      a.xy.inl[2 * t] = xy[2 * t];
+      a.xy.inl[2 * t + 1] = xy[2 * t + 1];
+      if (xy[2 * t] < 0 || xy[2 * t + 1] < 0 || xy[2 * t] + Tw > Wp || xy[2 * t + 1] + Th > Hp)
+        return fail(TB_ERR_ARG, "tb_deaugment_merge: tile %d at (%d,%d) leaves the %dx%d canvas", t, xy[2 * t],
+                    xy[2 * t + 1], Wp, Hp);
+    }
+  } else {
+    a.xy.dev = xy;
+  }
+  const long long blocks = (long long)n * a.nbx * a.nby;
+  if (blocks >= (1ll << 31)) return fail(TB_ERR_ARG, "tb_deaugment_merge: grid too large");
+  const bool al = (Th % 4 == 0) && (Tw % 4 == 0) && aligned16(pred) && aligned16(image) &&
+                  (!norm || aligned16(norm)) && (weight->kind != TB_W_TABLE || aligned16(weight->table));
+  if (al) {
+    TB_DISPATCH_TTA(tta, deaugment_merge_kernel<T, true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+  } else {
+    TB_DISPATCH_TTA(tta, deaugment_merge_kernel<T, false, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+  }
+  TB_LAUNCH_CHECK("deaugment_merge_kernel");
+  return TB_OK;
+}
+
+extern "C" {
+
+int tb_deaugment_merge(const void* pred, int dtype, const int32_t* xy, int xy_is_host, int n, int K, int Th, int Tw,
+                       int tta, int reduction, const tb_weight* weight, void* image, void* norm, int Hp, int Wp,
+                       void* stream) {
+  TB_REQUIRE(pred && xy && weight && image, TB_ERR_ARG, "tb_deaugment_merge: null pointer");
+  TB_REQUIRE(n >= 0 && K > 0 && Th > 0 && Tw > 0 && Hp >= Th && Wp >= Tw, TB_ERR_ARG,
+             "tb_deaugment_merge: bad shape");
+  TB_REQUIRE(reduction >= TB_RED_MEAN && reduction <= TB_RED_LOG1P, TB_ERR_ARG,
+             "tb_deaugment_merge: reduction must collapse the views (got %d)", reduction);
+  ViewSet views;
+  TB_REQUIRE(make_views(tta, &views), TB_ERR_ARG, "tb_deaugment_merge: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(views) || Th == Tw, TB_ERR_ARG, "tb_deaugment_merge: D4 needs square tiles");
+  if (n == 0) return TB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == TB_F32)
+    return launch_deaugment_merge<float>(pred, xy, xy_is_host, n, K, Th, Tw, tta, views, reduction, weight, image,
+                                         norm, Hp, Wp, s);
+  if (dtype == TB_F64)
+    return launch_deaugment_merge<double>(pred, xy, xy_is_host, n, K, Th, Tw, tta, views, reduction, weight, image,
+                                          norm, Hp, Wp, s);
+  return fail(TB_ERR_UNSUPPORTED, "tb_deaugment_merge: dtype must be TB_F32 or TB_F64 (got %d)", dtype);
+}
+
+int tb_normalize_crop(const void* image, const void* norm, int dtype, int K, int Hp, int Wp, int top, int left,
+                      int H, int W, double eps, void* out, void* stream) {
+  TB_REQUIRE(image && norm && out, TB_ERR_ARG, "tb_normalize_crop: null pointer");
+  TB_REQUIRE(K > 0 && H > 0 && W > 0 && top >= 0 && left >= 0 && top + H <= Hp && left + W <= Wp, TB_ERR_ARG,
+             "tb_normalize_crop: crop window outside the canvas");
+  const long long total = (long long)H * W;
+  const int gx = (int)std::min<long long>((total + kThreads - 1) / kThreads, (long long)sm_count() * 16);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == TB_F32)
+    normalize_crop_kernel<float><<<gx, kThreads, 0, s>>>((const float*)image, (const float*)norm, K, Hp, Wp, top,
+                                                          left, H, W, (float)eps, eps >= 0, (float*)out);
+  else if (dtype == TB_F64)
+    normalize_crop_kernel<double><<<gx, kThreads, 0, s>>>((const double*)image, (const double*)norm, K, Hp, Wp, top,
+                                                           left, H, W, eps, eps >= 0, (double*)out);
+  else
+    return fail(TB_ERR_UNSUPPORTED, "tb_normalize_crop: dtype must be TB_F32 or TB_F64 (got %d)", dtype);
+  TB_LAUNCH_CHECK("normalize_crop_kernel");
+  return TB_OK;
+}
+
+int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                 int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw,
+                 int top, int left, int H, int W, float* out_num, float* out_den, void* stream) {
+  TB_REQUIRE(grid && weight && out_num, TB_ERR_ARG, "tb_merge_all: null pointer");
+  TB_REQUIRE(pred || grid->tile_ptr, TB_ERR_ARG, "tb_merge_all: need pred or grid->tile_ptr");
+  TB_REQUIRE(!grid->tile_ptr || grid->tile_vstride, TB_ERR_ARG, "tb_merge_all: tile_ptr needs tile_vstride");
+  TB_REQUIRE(K > 0 && grid->nx > 0 && grid->ny > 0 && grid->Sx > 0 && grid->Sy > 0 && grid->Th > 0 && grid->Tw > 0 &&
+                 grid->n_slots > 0,
+             TB_ERR_ARG, "tb_merge_all: bad grid");
+  TB_REQUIRE(0 <= y0 && y0 < y1 && y1 <= Hp, TB_ERR_ARG, "tb_merge_all: bad row window [%d,%d) of %d", y0, y1, Hp);
+  TB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= grid->ny, TB_ERR_ARG, "tb_merge_all: bad tile-row window");
+  TB_REQUIRE((grid->nx - 1) * grid->Sx + grid->Tw <= Wp && (grid->ny - 1) * grid->Sy + grid->Th <= Hp, TB_ERR_ARG,
+             "tb_merge_all: grid exceeds the canvas");
+  TB_REQUIRE(reduction >= TB_RED_MEAN && reduction <= TB_RED_LOG1P, TB_ERR_ARG, "tb_merge_all: bad reduction %d",
+             reduction);
+  TB_REQUIRE(!raw || out_den, TB_ERR_ARG, "tb_merge_all: raw output needs out_den");
+  TB_REQUIRE((init_num == nullptr) == (init_den == nullptr), TB_ERR_ARG, "tb_merge_all: init_num/init_den mismatch");
+  TB_REQUIRE(raw || (top >= 0 && left >= 0 && H > 0 && W > 0 && top + H <= Hp && left + W <= Wp), TB_ERR_ARG,
+             "tb_merge_all: crop window outside the canvas");
+  MergeAllArgs a;
+  TB_REQUIRE(make_views(tta, &a.views), TB_ERR_ARG, "tb_merge_all: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(a.views) || grid->Th == grid->Tw, TB_ERR_ARG, "tb_merge_all: D4 needs square tiles");
+  TB_REQUIRE(make_weight<float>(weight, grid->Th, grid->Tw, &a.w), TB_ERR_ARG, "tb_merge_all: bad weight spec");
+  a.pred = pred; a.grid = *grid; a.K = K; a.red = reduction; a.Hp = Hp; a.Wp = Wp;
+  a.y0 = y0; a.y1 = y1; a.r0 = r0; a.r1 = r1; a.raw = raw; a.top = top; a.left = left; a.H = H; a.W = W;
+  a.init_num = init_num; a.init_den = init_den; a.out_num = out_num; a.out_den = out_den;
+  // block window: rows from floor(y0/BS) to ceil(y1/BS); columns cover the crop (or the whole canvas when raw)
+  const int xa = raw ? 0 : left, xb = raw ? Wp : left + W;
+  a.bx0 = xa / BS;
+  a.nbx = (xb + BS - 1) / BS - a.bx0;
+  a.nby = (y1 + BS - 1) / BS - y0 / BS;
+  const long long blocks = (long long)a.nbx * a.nby;
+  TB_REQUIRE(blocks > 0 && blocks < (1ll << 31), TB_ERR_ARG, "tb_merge_all: grid too large");
+  const bool al = (grid->Th % 4 == 0) && (grid->Tw % 4 == 0) && (grid->Sx % 4 == 0) && (grid->Sy % 4 == 0) &&
+                  (!pred || aligned16(pred)) && !grid->tile_ptr && aligned16(out_num) &&
+                  (weight->kind != TB_W_TABLE || aligned16(weight->table));
+  // with a pointer table the caller vouches for 16-byte aligned planes via tile_vstride % 4 == 0 (checked by the shim)
+  const bool al_tbl = grid->tile_ptr && (grid->Th % 4 == 0) && (grid->Tw % 4 == 0) && (grid->Sx % 4 == 0) &&
+                      (grid->Sy % 4 == 0) && aligned16(out_num) &&
+                      (weight->kind != TB_W_TABLE || aligned16(weight->table));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (al || al_tbl) {
+    TB_DISPATCH_TTA(tta, merge_all_kernel<true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+  } else {
+    TB_DISPATCH_TTA(tta, merge_all_kernel<false, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
+  }
+  TB_LAUNCH_CHECK("merge_all_kernel");
+  return TB_OK;
+}
+
+int tb_standin_model(const float* x, int B, int Cin, int K, int Th, int Tw, const float* Wm_host, float* y,
+                     void* stream) {
+  TB_REQUIRE(x && y && Wm_host, TB_ERR_ARG, "tb_standin_model: null pointer");
+  TB_REQUIRE(B >= 0 && Cin > 0 && Cin <= 8 && K > 0 && K * Cin <= 64 && Th > 0 && Tw > 0 && (Th * Tw) % 4 == 0 &&
+                 Tw % 4 == 0,
+             TB_ERR_ARG, "tb_standin_model: bad shape");
+  if (B == 0) return TB_OK;
+  StandinArgs a;
+  a.x = x; a.y = y; a.B = B; a.Cin = Cin; a.K = K; a.Th = Th; a.Tw = Tw;
+  for (int i = 0; i < K * Cin; ++i) a.Wm[i] = Wm_host[i];
+  const size_t total = (size_t)B * Th * Tw / 4;
+  const int gx = (int)std::min<size_t>((total + kThreads - 1) / kThreads, (size_t)sm_count() * 32);
+  standin_model_kernel<<<gx, kThreads, 0, (cudaStream_t)stream>>>(a);
+  TB_LAUNCH_CHECK("standin_model_kernel");
+  return TB_OK;
+}
+
+}  // extern "C"

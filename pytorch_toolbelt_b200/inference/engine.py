@@ -1,0 +1,281 @@
+"""Fused B200 tiled-inference pipeline (new API; the reference has only the Python loop of README.md:196-227).
+
+    engine = TiledInferenceEngine(image.shape, tile_size=512, tile_step=256, channels=4, weight="pyramid", tta="d4")
+    logits = engine.predict(image, model, batch_size=8)          # [K,H,W] float32 on the GPU
+
+Two kernels bracket the (black-box) model:
+
+* ``slice``  : image resident in HBM -> crop + border + HWC->CHW + cast + per-channel affine + all TTA views,
+               one launch, written once as the model's input batch (tb_slice_augment);
+* ``merge``  : all model outputs -> inverse TTA permutation + view reduction + tile weight + overlap-add +
+               normalisation + margin crop, one launch, output-stationary: every prediction element is read
+               once, every output pixel written once, no atomics and no canvas / norm_mask in memory
+               (tb_merge_all). Accumulation follows the reference's tile order, so the result matches
+               ``TileMerger`` fed in row-major order bit for bit (given the same per-tile values).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .._native import TB
+from .tiles import BORDER_CONSTANT, ImageSlicer
+
+__all__ = ["TiledInferenceEngine", "tta_code"]
+
+_TTA_NAMES = {
+    None: TB.TTA_NONE,
+    "none": TB.TTA_NONE,
+    "fliplr": TB.TTA_FLIPLR,
+    "flipud": TB.TTA_FLIPUD,
+    "flips": TB.TTA_FLIPS,
+    "d2": TB.TTA_D2,
+    "d4": TB.TTA_D4,
+}
+
+
+def tta_code(tta) -> int:
+    if isinstance(tta, int) and not isinstance(tta, bool):
+        if tta not in TB.TTA_VIEWS:
+            raise ValueError(f"Unknown TTA code {tta}")
+        return tta
+    if tta not in _TTA_NAMES:
+        raise ValueError(f"Unknown TTA group {tta!r}; expected one of {sorted(k for k in _TTA_NAMES if k)}")
+    return _TTA_NAMES[tta]
+
+
+class TiledInferenceEngine:
+    def __init__(
+        self,
+        image_shape: Sequence[int],
+        tile_size,
+        tile_step,
+        channels: int,
+        weight: Union[str, np.ndarray] = "pyramid",
+        tta=None,
+        reduction: str = "mean",
+        image_margin=0,
+        border_type: int = BORDER_CONSTANT,
+        border_value=0,
+        scale: Optional[Sequence[float]] = None,
+        bias: Optional[Sequence[float]] = None,
+        analytic_weight: bool = False,
+        device: Optional[Union[str, torch.device]] = None,
+    ):
+        """
+        :param image_shape: (H, W[, C]) of the source image
+        :param channels: number of model output channels K
+        :param weight: "mean" | "pyramid" | "gaussian" | ndarray [Th,Tw]
+        :param tta: None | "fliplr" | "flipud" | "flips" | "d2" | "d4"
+        :param reduction: how TTA views are averaged ("mean", "sum", "gmean", "hmean", "harmonic1p", "logodd", "log1p")
+        :param scale, bias: optional per-input-channel affine applied while slicing: x = float(pixel)*scale[c] + bias[c]
+        :param analytic_weight: regenerate "pyramid"/"gaussian"/"mean" weights in registers (fp32, <= 3e-7 relative
+               to the float64->float32 table) instead of reading the table
+        """
+        N.require_cuda("TiledInferenceEngine")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.slicer = ImageSlicer(image_shape, tile_size, tile_step, image_margin=image_margin, weight=weight)
+        self.channels = int(channels)
+        self.tta = tta_code(tta)
+        self.views = TB.TTA_VIEWS[self.tta]
+        if reduction not in TB.REDUCTIONS or TB.REDUCTIONS[reduction] == TB.RED_NONE:
+            raise KeyError(f"Unsupported reduction mode {reduction}")
+        self.reduction = TB.REDUCTIONS[reduction]
+        th, tw = self.slicer.tile_size
+        if self.tta == TB.TTA_D4 and th != tw:
+            raise ValueError(f"D4 TTA needs square tiles, got {th}x{tw}")
+        self.border_type = int(border_type)
+        vals = list(border_value)[:4] if isinstance(border_value, (tuple, list, np.ndarray)) else [border_value]
+        self._border_value = N.float_array(vals, 4)
+        self._scale, self._bias = scale, bias
+        self.num_tiles = len(self.slicer.crops)
+        self._bbox_xy = N.as_dev_xy(self.slicer.bbox_crops, self.device)
+        self._weight_table = torch.from_numpy(np.asarray(self.slicer.weight, dtype=np.float32)).to(self.device).contiguous()
+        if analytic_weight and self.slicer.weight_kind != TB.W_TABLE:
+            self._weight = N.Weight(self.slicer.weight_kind, None, float(self.slicer.weight_param))
+        else:
+            self._weight = N.Weight(TB.W_TABLE, self._weight_table.data_ptr(), 0.0)
+        ny, nx = self.slicer.grid_shape
+        sh, sw = self.slicer.tile_step
+        self._grid_dims = (nx, ny, sw, sh, th, tw)
+        self._keepalive: List[torch.Tensor] = []
+
+    # ------------------------------------------------------------------ image upload
+    def to_device(self, image: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
+        """Host ndarray / CPU tensor -> contiguous CUDA tensor (HWC or HW), dtype preserved."""
+        if isinstance(image, np.ndarray):
+            image = torch.from_numpy(np.ascontiguousarray(image))
+        if not image.is_cuda:
+            image = image.to(self.device, non_blocking=True)
+        return image.contiguous()
+
+    # ------------------------------------------------------------------ slice (+augment)
+    def slice(self, image: torch.Tensor, start: int = 0, stop: Optional[int] = None, layout: str = "HWC",
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Tiles [start, stop) of the grid as the model input batch: float32 [A*n, C, Th, Tw], aug-major."""
+        stop = self.num_tiles if stop is None else stop
+        n = stop - start
+        if not (0 <= start <= stop <= self.num_tiles):
+            raise IndexError(f"tile range [{start},{stop}) outside [0,{self.num_tiles})")
+        if not image.is_cuda:
+            raise ValueError("slice() expects the image resident on the GPU; call to_device() first")
+        image = image.contiguous()
+        if layout == "HWC":
+            h, w = image.shape[0], image.shape[1]
+            c = 1 if image.dim() == 2 else image.shape[2]
+            layout_code = TB.HWC
+        elif layout == "CHW":
+            c, h, w = image.shape
+            layout_code = TB.CHW
+        else:
+            raise ValueError("layout must be 'HWC' or 'CHW'")
+        if h != self.slicer.image_height or w != self.slicer.image_width:
+            raise ValueError(f"image is {h}x{w}, engine was built for {self.slicer.image_height}x{self.slicer.image_width}")
+        if image.dtype not in TB.TORCH_DTYPE:
+            raise TypeError(f"unsupported image dtype {image.dtype}")
+        th, tw = self.slicer.tile_size
+        shape = (self.views * n, c, th, tw)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=image.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 tensor of shape {shape}")
+        if n == 0:
+            return out
+        xy = self._bbox_xy[start:stop]
+        with torch.cuda.device(image.device):
+            rc = N.lib().tb_slice_augment(
+                image.data_ptr(), TB.TORCH_DTYPE[image.dtype], layout_code, h, w, c, xy.data_ptr(), n, th, tw, self.tta,
+                self.border_type, self._border_value, N.float_array(self._scale, c) if self._scale is not None else None,
+                N.float_array(self._bias, c) if self._bias is not None else None, out.data_ptr(),
+                N.stream_ptr(image.device),
+            )
+        N.check(rc, "tb_slice_augment")
+        return out
+
+    # ------------------------------------------------------------------ merge
+    def _grid(self, n_slots: int) -> N.Grid:
+        nx, ny, sw, sh, th, tw = self._grid_dims
+        return N.Grid(nx, ny, sw, sh, th, tw, n_slots, None, None, None)
+
+    def merge(
+        self,
+        preds: Union[torch.Tensor, Sequence[torch.Tensor]],
+        out: Optional[torch.Tensor] = None,
+        rows: Optional[Tuple[int, int]] = None,
+        tile_rows: Optional[Tuple[int, int]] = None,
+        raw: bool = False,
+        init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    ):
+        """All predictions -> merged, normalised, cropped logits float32 [K,H,W].
+
+        ``preds`` is either one tensor [A*N,K,Th,Tw] (aug-major over the whole grid) or the list of the model's
+        per-batch outputs ([A*b,K,Th,Tw] each, batches in grid order) -- the latter is merged in place through a
+        pointer table, without concatenating.
+
+        Band mode (multi-GPU strips): ``rows=(y0,y1)`` canvas rows to produce, ``tile_rows=(r0,r1)`` contributing
+        tile rows, ``raw=True`` returns un-normalised ``(num [K,y1-y0,Wp], den [y1-y0,Wp])``, ``init`` seeds the
+        accumulation with such a pair (the halo received from the previous strip).
+        """
+        nx, ny, sw, sh, th, tw = self._grid_dims
+        hp, wp = self.slicer.target_shape
+        k = self.channels
+        y0, y1 = rows if rows is not None else (0, hp)
+        r0, r1 = tile_rows if tile_rows is not None else (0, ny)
+        grid = self._grid(self.num_tiles)
+        keep = []
+        if torch.is_tensor(preds):
+            p = preds
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                raise ValueError("preds must be a contiguous float32 CUDA tensor")
+            if tuple(p.shape[1:]) != (k, th, tw) or p.shape[0] % self.views != 0:
+                raise ValueError(f"preds must be [A*n,{k},{th},{tw}], got {tuple(p.shape)}")
+            n_slots = p.shape[0] // self.views
+            if n_slots != self.num_tiles and tile_rows is None:
+                raise ValueError(f"preds holds {n_slots} tiles per view, the grid has {self.num_tiles}")
+            grid.n_slots = n_slots
+            if n_slots != self.num_tiles:
+                # band mode with only the band's tiles resident: slot = tile - r0*nx
+                slots = np.full(self.num_tiles, -1, dtype=np.int32)
+                slots[r0 * nx : r0 * nx + n_slots] = np.arange(n_slots, dtype=np.int32)
+                slot_dev = torch.from_numpy(slots).to(p.device)
+                keep.append(slot_dev)
+                grid.tile_slot = slot_dev.data_ptr()
+            pred_ptr, device = p.data_ptr(), p.device
+        else:
+            ptrs = np.zeros(self.num_tiles, dtype=np.int64)
+            vstr = np.zeros(self.num_tiles, dtype=np.int64)
+            t = r0 * nx if tile_rows is not None else 0
+            plane_set = k * th * tw
+            device = preds[0].device
+            for batch in preds:
+                if batch.dtype != torch.float32 or not batch.is_contiguous() or not batch.is_cuda:
+                    raise ValueError("every prediction batch must be a contiguous float32 CUDA tensor")
+                if tuple(batch.shape[1:]) != (k, th, tw) or batch.shape[0] % self.views != 0:
+                    raise ValueError(f"prediction batches must be [A*b,{k},{th},{tw}], got {tuple(batch.shape)}")
+                b = batch.shape[0] // self.views
+                base = batch.data_ptr()
+                if base % 16 != 0:
+                    raise ValueError("prediction batches must be 16-byte aligned")
+                ptrs[t : t + b] = base + np.arange(b, dtype=np.int64) * (plane_set * 4)
+                vstr[t : t + b] = b * plane_set
+                t += b
+            expected = (r1 * nx) if tile_rows is not None else self.num_tiles
+            if t != expected:
+                raise ValueError(f"prediction batches cover {t} tiles, expected {expected}")
+            ptr_dev = torch.from_numpy(ptrs).to(device)
+            vstr_dev = torch.from_numpy(vstr).to(device)
+            keep += [ptr_dev, vstr_dev]
+            grid.tile_ptr = ptr_dev.data_ptr()
+            grid.tile_vstride = vstr_dev.data_ptr()
+            pred_ptr = None
+        top, left = self.slicer.margin_top, self.slicer.margin_left
+        h, w = self.slicer.image_height, self.slicer.image_width
+        init_num = init_den = None
+        if init is not None:
+            init_num, init_den = init
+            if tuple(init_num.shape) != (k, y1 - y0, wp) or tuple(init_den.shape) != (y1 - y0, wp):
+                raise ValueError("init must be (num [K,rows,Wp], den [rows,Wp])")
+            init_num, init_den = init_num.contiguous(), init_den.contiguous()
+        if raw:
+            num = torch.empty((k, y1 - y0, wp), dtype=torch.float32, device=device)
+            den = torch.empty((y1 - y0, wp), dtype=torch.float32, device=device)
+            out_num, out_den, result = num.data_ptr(), den.data_ptr(), (num, den)
+        else:
+            if out is None:
+                out = torch.empty((k, h, w), dtype=torch.float32, device=device)
+            elif tuple(out.shape) != (k, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous float32 tensor [{k},{h},{w}]")
+            out_num, out_den, result = out.data_ptr(), None, out
+        with torch.cuda.device(device):
+            rc = N.lib().tb_merge_all(
+                pred_ptr, C.byref(grid), k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1,
+                N.ptr(init_num), N.ptr(init_den), 1 if raw else 0, top, left, h, w, out_num, out_den,
+                N.stream_ptr(device),
+            )
+        N.check(rc, "tb_merge_all")
+        # tables must outlive the asynchronous launch: park them until the next call on this engine
+        self._keepalive = keep
+        return result
+
+    # ------------------------------------------------------------------ whole pipeline
+    @torch.no_grad()
+    def predict(self, image: Union[np.ndarray, torch.Tensor], model: Callable[[torch.Tensor], torch.Tensor],
+                batch_size: Optional[int] = None, layout: str = "HWC") -> torch.Tensor:
+        """image (host or device) -> [K,H,W] float32 logits on the GPU. ``batch_size`` counts tiles (each
+        contributes A views to the model batch); None = all tiles in one model call."""
+        image = self.to_device(image)
+        batch_size = self.num_tiles if batch_size is None else int(batch_size)
+        outputs = []
+        for start in range(0, self.num_tiles, batch_size):
+            stop = min(start + batch_size, self.num_tiles)
+            pred = model(self.slice(image, start, stop, layout=layout))
+            if pred.dtype != torch.float32:
+                pred = pred.float()
+            outputs.append(pred.contiguous())
+        return self.merge(outputs[0] if len(outputs) == 1 else outputs)

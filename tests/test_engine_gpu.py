@@ -1,0 +1,181 @@
+"""GPU: the fused pipeline (slice+augment kernel, output-stationary merge kernel) against the oracle's restatement
+of the reference loop, plus size-independent properties at the BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as OP
+from oracle import tiles_oracle as TO
+from oracle import tta_oracle as AO
+from pytorch_toolbelt_b200 import _native as N
+from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine
+from pytorch_toolbelt_b200.inference.tiles import CudaTileMerger, ImageSlicer
+
+pytestmark = pytest.mark.gpu
+
+
+def standin_cuda(x, Wm):
+    B, C, T, T2 = x.shape
+    y = torch.empty((B, Wm.shape[0], T, T2), dtype=torch.float32, device=x.device)
+    import ctypes as C_
+
+    arr = (C_.c_float * Wm.numel())(*[float(v) for v in Wm.flatten().tolist()])
+    N.check(N.lib().tb_standin_model(x.data_ptr(), B, C, Wm.shape[0], T, T2, arr, y.data_ptr(), N.stream_ptr(x.device)),
+            "standin")
+    return y
+
+
+def buffer_close(ours, ref, rel=1e-5):
+    ours, ref = ours.double().cpu(), ref.double().cpu()
+    scale = ref.abs().max().item()
+    err = (ours - ref).abs().max().item()
+    assert err <= rel * scale, (err, scale)
+
+
+@pytest.mark.parametrize(
+    "shape,tile,step,group,K,weight",
+    [
+        ((300, 260, 3), 64, 32, "d4", 4, "pyramid"),
+        ((300, 260, 3), 64, 32, "none", 3, "pyramid"),
+        ((257, 301, 1), (64, 32), (32, 32), "flips", 2, "mean"),
+        ((200, 200, 3), 51, 26, "d2", 2, "pyramid"),       # odd tile size: scalar (unaligned) kernels
+        ((200, 200, 3), 50, 20, "d4", 2, "gaussian"),      # stride not a multiple of 4, 3-fold overlap
+        ((130, 120, 4), 128, 128, "fliplr", 1, "pyramid"),  # single tile bigger than the image
+    ],
+)
+def test_pipeline_vs_oracle(shape, tile, step, group, K, weight):
+    rng = np.random.default_rng(0)
+    image = rng.integers(0, 256, shape).astype(np.uint8)
+    Cin = shape[2]
+    Wm = OP.standin_model_weights(K, Cin)
+    # slice + augment: bit-exact against split -> HWC->CHW -> float -> *_image_augment
+    eng = TiledInferenceEngine(image.shape, tile, step, channels=K, weight=weight, tta=None if group == "none" else group)
+    dev_img = eng.to_device(image)
+    aug = eng.slice(dev_img)
+    t2 = (tile, tile) if np.isscalar(tile) else tile
+    s2 = (step, step) if np.isscalar(step) else step
+    grid = TO.tile_grid(shape[0], shape[1], t2, s2)
+    tiles = TO.split(image, grid)
+    batch = torch.stack([torch.from_numpy(np.ascontiguousarray(np.moveaxis(t.reshape(t2[0], t2[1], Cin), -1, 0))) for t in tiles]).float()
+    ref_aug = AO.augment(batch, group) if group != "none" else batch
+    assert torch.equal(aug.cpu(), ref_aug)
+    # identical predictions on both sides (computed once on the CPU)
+    pred = OP.standin_model(ref_aug, Wm)
+    ours = eng.merge(pred.cuda())
+    ref = OP.tiled_inference_cpu(image, t2, s2, K, weight=weight, group=group, batch_size=5,
+                                 model=lambda x: OP.standin_model(x, Wm))
+    assert ours.shape == ref.shape == (K, shape[0], shape[1])
+    buffer_close(ours, ref, rel=2e-6)
+    # batch-list form (pointer table) gives the same bits as the single-tensor form
+    A = eng.views
+    n = eng.num_tiles
+    batches = []
+    for s in range(0, n, 5):
+        e = min(s + 5, n)
+        batches.append(pred.view(A, n, K, t2[0], t2[1])[:, s:e].reshape(-1, K, t2[0], t2[1]).contiguous().cuda())
+    assert torch.equal(eng.merge(batches), ours)
+    # streaming TileMerger path with fused de-augment agrees too
+    slicer = ImageSlicer(image.shape, tile, step, weight=weight)
+    m = CudaTileMerger(slicer.target_shape, K, slicer.weight)
+    for b, s in zip(batches, range(0, n, 5)):
+        m.integrate_batch(b, slicer.crops[s : s + 5], tta=eng.tta)
+    top, left = slicer.margin_top, slicer.margin_left
+    streamed = m.merge()[:, top : top + shape[0], left : left + shape[1]]
+    buffer_close(streamed, ref, rel=1e-5)
+
+
+def test_predict_end_to_end_with_cuda_model():
+    rng = np.random.default_rng(4)
+    image = rng.integers(0, 256, (500, 420, 3)).astype(np.uint8)
+    K = 4
+    Wm = OP.standin_model_weights(K, 3)
+    eng = TiledInferenceEngine(image.shape, 128, 64, channels=K, weight="pyramid", tta="d4")
+    out = eng.predict(image, lambda x: standin_cuda(x, Wm), batch_size=7)
+    ref = OP.tiled_inference_cpu(image, 128, 64, K, weight="pyramid", group="d4")
+    buffer_close(out, ref, rel=1e-5)
+
+
+def test_analytic_weights_match_tables():
+    rng = np.random.default_rng(8)
+    image = rng.integers(0, 256, (300, 300, 3)).astype(np.uint8)
+    for weight in ("pyramid", "gaussian", "mean"):
+        a = TiledInferenceEngine(image.shape, 64, 32, channels=2, weight=weight, tta="fliplr", analytic_weight=True)
+        b = TiledInferenceEngine(image.shape, 64, 32, channels=2, weight=weight, tta="fliplr", analytic_weight=False)
+        pred = torch.randn(2 * a.num_tiles, 2, 64, 64, generator=torch.Generator().manual_seed(0)).cuda() * 3
+        buffer_close(a.merge(pred), b.merge(pred), rel=1e-5)
+
+
+def test_slice_options_borders_affine_layout():
+    rng = np.random.default_rng(9)
+    image = rng.integers(0, 256, (150, 170, 3)).astype(np.uint8)
+    grid = TO.tile_grid(150, 170, (64, 64), (48, 48))
+    for mode in (0, 1, 2, 3, 4):
+        eng = TiledInferenceEngine(image.shape, 64, 48, channels=1, tta=None, border_type=mode, border_value=(5, 6, 7))
+        out = eng.slice(eng.to_device(image))
+        ref = np.stack(TO.split(image, grid, mode, (5, 6, 7)))
+        assert np.array_equal(out.cpu().numpy(), np.moveaxis(ref, -1, 1).astype(np.float32)), mode
+    scale, bias = [1 / 58.0, 1 / 57.0, 1 / 57.5], [-2.1, -2.0, -1.8]
+    eng = TiledInferenceEngine(image.shape, 64, 48, channels=1, tta="d2", scale=scale, bias=bias)
+    out = eng.slice(eng.to_device(image))
+    base = np.moveaxis(np.stack(TO.split(image, grid)), -1, 1).astype(np.float32)
+    norm = base * np.array(scale, np.float32)[None, :, None, None] + np.array(bias, np.float32)[None, :, None, None]
+    assert torch.equal(out.cpu(), AO.augment(torch.from_numpy(norm), "d2"))
+    chw = torch.from_numpy(np.ascontiguousarray(np.moveaxis(image, -1, 0))).float().cuda()
+    eng = TiledInferenceEngine(image.shape, 64, 48, channels=1, tta=None)
+    assert np.array_equal(eng.slice(chw, layout="CHW").cpu().numpy(), base)
+    assert np.array_equal(eng.slice(eng.to_device(image), 3, 7).cpu().numpy(), base[3:7])
+
+
+def test_band_mode_reproduces_full_merge():
+    """Strip partition used by the multi-GPU path: bands + halo seed == single full merge, bit for bit."""
+    rng = np.random.default_rng(12)
+    image_shape = (700, 500, 3)
+    K = 3
+    eng = TiledInferenceEngine(image_shape, 128, 64, channels=K, weight="pyramid", tta="flips")
+    ny, nx = eng.slicer.grid_shape
+    pred = torch.randn(eng.views * eng.num_tiles, K, 128, 128, generator=torch.Generator().manual_seed(1)).cuda()
+    full = eng.merge(pred)
+    hp, wp = eng.slicer.target_shape
+    r_split = ny // 2
+    y_split = r_split * 64
+    # strip 0 owns tile rows [0,r_split) and canvas rows [0,y_split); its tiles spill into [y_split, y_split+64)
+    top_part = eng.merge(pred, rows=(0, y_split), tile_rows=(0, r_split))
+    halo = eng.merge(pred, rows=(y_split, y_split + 64), tile_rows=(0, r_split), raw=True)
+    # strip 1 owns the rest; the first 64 rows start from the halo
+    seeded = eng.merge(pred, rows=(y_split, y_split + 64), tile_rows=(r_split, ny), init=halo)
+    rest = eng.merge(pred, rows=(y_split + 64, hp), tile_rows=(r_split, ny))
+    top = eng.slicer.margin_top
+    H = image_shape[0]
+
+    def rows_of(t, y0, y1):
+        a, b = max(y0 - top, 0), min(y1 - top, H)
+        return t[:, a:b]
+
+    assert torch.equal(rows_of(top_part, 0, y_split), rows_of(full, 0, y_split))
+    assert torch.equal(rows_of(seeded, y_split, y_split + 64), rows_of(full, y_split, y_split + 64))
+    assert torch.equal(rows_of(rest, y_split + 64, hp), rows_of(full, y_split + 64, hp))
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg 2 geometry (5000x5000x3, 512/256, d4, K=4) through size-independent properties:
+    constant predictions merge to the constant; D4 de-augment of an augmented constant-per-view field is exact;
+    slice->identity-model->merge reproduces the image (weights cancel)."""
+    H = W = 5000
+    rng = np.random.default_rng(0)
+    image = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+    eng = TiledInferenceEngine(image.shape, 512, 256, channels=3, weight="pyramid", tta="d4")
+    assert eng.num_tiles == 361 and eng.slicer.target_shape == (5120, 5120)
+    dev = eng.to_device(image)
+    aug = eng.slice(dev)  # [8*361,3,512,512] = 9.1 GB
+    assert aug.shape == (8 * 361, 3, 512, 512)
+    # identity model: de-augmented views all equal the tile, the weighted mean of equal values is the value
+    out = eng.merge(aug)
+    ref = torch.from_numpy(np.ascontiguousarray(np.moveaxis(image, -1, 0))).float()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-3)
+    del aug, out
+    torch.cuda.empty_cache()
+    # checksum of the tile stream: every view holds a permutation of the same pixels
+    eng1 = TiledInferenceEngine(image.shape, 512, 256, channels=1, weight="mean", tta="d4")
+    a = eng1.slice(dev, 100, 104)
+    sums = a.view(8, 4, -1).double().sum(-1)
+    assert torch.equal(sums, sums[0:1].expand(8, 4))
