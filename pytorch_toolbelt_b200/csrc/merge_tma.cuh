@@ -1,0 +1,73 @@
+// TMA + mbarrier pipelined variant of the output-stationary merge (sm_100a).
+//
+// The generic merge_all_kernel is latency-bound: each CTA alternates "issue 8 loads / wait / reduce" and
+// its register footprint caps occupancy at 2 CTAs per SM. Here a producer lane streams the 32x32 fp32 boxes
+// of all A views of a (channel, tile) pair into a ring of shared-memory stages with cp.async.bulk.tensor
+// (TMA); 8 consumer warps reduce stage s while stages s+1.. are in flight. Bytes in flight are set by the
+// ring depth (3 x 32 KB per CTA for D4), not by occupancy, and the load side costs one instruction per 4 KB.
+//
+// Shared-memory boxes use the TMA 128-byte swizzle (row = 32 floats = 128 B): 16-byte chunk j of row r
+// lives at chunk j ^ (r & 7). Consumer lanes are mapped (lane>>2 -> row&7, lane&3 -> column&3) so that
+// row-wise (non-transposing views) reads are bank-conflict free and column-wise (transposing views) reads
+// are at most 2-way conflicted.
+#pragma once
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;  // + 1 producer warp
+constexpr int kBoxFloats = 32 * 32;
+constexpr int kBoxBytes = kBoxFloats * 4;
+
+__host__ __device__ constexpr int tma_stages(int views) { return views >= 8 ? 3 : (views >= 3 ? 6 : 10); }
+__host__ __device__ constexpr size_t tma_smem_bytes(int views) {
+  return (size_t)tma_stages(views) * views * kBoxBytes + 1024 /*alignment slack*/ + 2 * 16 * sizeof(uint64_t);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 2-D tiled TMA load: box (32 cols x 32 rows) at (col, row) -> shared memory, completion on `bar`.
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(row)
+      : "memory");
+}
+
+// float index of element (rr, cc) inside a 128B-swizzled 32x32 fp32 box
+__device__ __forceinline__ int swz(int rr, int cc) { return rr * 32 + ((((cc >> 2) ^ (rr & 7)) << 2) | (cc & 3)); }
+
+struct MergeAllArgs;  // defined in tiles.cu
+
+}  // namespace tb

@@ -13,10 +13,13 @@
 //   (whole loop)                                          -> merge_all_kernel (output-stationary)
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <utility>
 
 #include "common.cuh"
+#include "merge_tma.cuh"
 
 namespace tb {
 
@@ -423,6 +426,95 @@ __device__ __forceinline__ void deaug_reduce4(const T* __restrict__ plane0, size
   for (int e = 0; e < 4; ++e) out[e] = red_post<T>(red, acc[e], COUNT);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 2b. fast slice + augment for tiles whose sides are multiples of 32 (every block is full):
+// compile-time view codes, per-thread offsets computed once, up to 4 channels resident in shared memory
+// per pass. ~10 instructions per 16-byte store instead of ~200 in the generic kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunkC = 4;
+constexpr int CH_STRIDE = BS * PITCH + 1;  // +1: channel planes start in different banks
+
+template <typename SrcT>
+__device__ __forceinline__ void load_block_fast(const SliceArgs& a, const SrcT* __restrict__ img, int x0, int y0,
+                                                int R0, int C0, int c0, int cc, float* sm) {
+  const int lr = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const int gy = y0 + R0 + lr, gx = x0 + C0 + 4 * lq;
+  const bool interior = (y0 + R0 >= 0) && (y0 + R0 + BS <= a.H) && (x0 + C0 >= 0) && (x0 + C0 + BS <= a.W);
+  const int sy = interior ? gy : border_remap(gy, 0, a.H, a.border);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int sx = interior ? gx + e : border_remap(gx + e, 0, a.W, a.border);
+    const bool fill = (sy < 0 || sx < 0);
+    for (int ch = 0; ch < cc; ++ch) {
+      const int c = c0 + ch;
+      float v;
+      if (fill) {
+        v = c < 4 ? a.bval[c] : 0.f;
+      } else if (a.layout == TB_HWC) {
+        v = to_f32(img[((size_t)sy * a.W + sx) * a.C + c]);
+      } else {
+        v = to_f32(img[((size_t)c * a.H + sy) * a.W + sx]);
+      }
+      if (a.has_affine && c < 8) v = __fadd_rn(__fmul_rn(v, a.scale[c]), a.bias[c]);
+      sm[ch * CH_STRIDE + lr * PITCH + 4 * lq + e] = v;
+    }
+  }
+}
+
+template <typename SrcT, int TTA>
+__global__ void __launch_bounds__(kThreads) slice_augment_fast_kernel(SliceArgs a) {
+  using V = Views<TTA>;
+  __shared__ float sm[kChunkC * CH_STRIDE];
+  const int per_tile = a.nbx * a.nby;
+  const int t = blockIdx.x / per_tile;
+  const int blk = blockIdx.x - t * per_tile;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int R0 = by * BS, C0 = bx * BS;
+  const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+  const SrcT* img = static_cast<const SrcT*>(a.img);
+  const size_t plane = (size_t)a.Th * a.Tw;
+  const size_t view_stride = (size_t)a.n * a.C * plane;
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+
+  for (int c0 = 0; c0 < a.C; c0 += kChunkC) {
+    const int cc = min(kChunkC, a.C - c0);
+    if (c0) __syncthreads();
+    load_block_fast<SrcT>(a, img, x0, y0, R0, C0, c0, cc, sm);
+    __syncthreads();
+#pragma unroll
+    for (int va = 0; va < V::count; ++va) {
+      constexpr unsigned packed = V::packed;
+      const unsigned code = (packed >> (3 * va)) & 7u;
+      // shared-memory index of element e of this thread's 4-group: base + e*step
+      int base, step, oi0, oj0;
+      if (code & V_T) {
+        // out[i,j] = src[(FI ? M-j : j), (FJ ? M-i : i)]: row varies with j, column with i
+        const int col = (code & V_FJ) ? (BS - 1 - li) : li;
+        const int row0 = (code & V_FI) ? (BS - 1 - 4 * lq) : 4 * lq;
+        base = row0 * PITCH + col;
+        step = (code & V_FI) ? -PITCH : PITCH;
+        oi0 = (code & V_FJ) ? a.Tw - C0 - BS : C0;
+        oj0 = (code & V_FI) ? a.Th - R0 - BS : R0;
+      } else {
+        const int row = (code & V_FI) ? (BS - 1 - li) : li;
+        const int col0 = (code & V_FJ) ? (BS - 1 - 4 * lq) : 4 * lq;
+        base = row * PITCH + col0;
+        step = (code & V_FJ) ? -1 : 1;
+        oi0 = (code & V_FI) ? a.Th - R0 - BS : R0;
+        oj0 = (code & V_FJ) ? a.Tw - C0 - BS : C0;
+      }
+      float* o = a.out + (size_t)va * view_stride + ((size_t)t * a.C + c0) * plane + (size_t)(oi0 + li) * a.Tw + oj0 +
+                 4 * lq;
+      for (int ch = 0; ch < cc; ++ch) {
+        const float* s = sm + ch * CH_STRIDE + base;
+        const float4 q = make_float4(s[0], s[step], s[2 * step], s[3 * step]);
+        *reinterpret_cast<float4*>(o + (size_t)ch * plane) = q;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. stand-alone TTA de-augment (+ reduction)
 // ------------------------------------------------------------------------------------------------
@@ -684,6 +776,174 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 7b. TMA-pipelined output-stationary merge (requires Th, Tw, Sx, Sy multiples of 32 and a single pred tensor)
+// ------------------------------------------------------------------------------------------------
+template <int TTA>
+__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ CUtensorMap tmap) {
+  using V = Views<TTA>;
+  constexpr int NV = V::count;
+  constexpr int STAGES = tma_stages(NV);
+  extern __shared__ unsigned char smem_raw[];
+  // boxes must be 1024-byte aligned for the 128-byte swizzle atom
+  float* boxes = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(boxes + (size_t)STAGES * NV * kBoxFloats);
+  uint64_t* empty = full + STAGES;
+
+  const tb_grid& g = a.grid;
+  const int by = blockIdx.x / a.nbx, bxi = blockIdx.x - by * a.nbx;
+  const int Y0 = a.y0 - (a.y0 % BS) + by * BS;
+  const int X0 = (a.bx0 + bxi) * BS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // covering tiles (every 32x32 canvas block lies fully inside each tile that touches it)
+  int ra = (Y0 - g.Th + g.Sy) / g.Sy;
+  if (Y0 - g.Th + 1 <= 0) ra = 0;
+  int rb = (Y0 + BS - 1) / g.Sy;
+  ra = max(ra, a.r0);
+  rb = min(rb, min(g.ny, a.r1) - 1);
+  int ca = (X0 - g.Tw + g.Sx) / g.Sx;
+  if (X0 - g.Tw + 1 <= 0) ca = 0;
+  const int cb = min((X0 + BS - 1) / g.Sx, g.nx - 1);
+
+  if (warp == kTmaConsumerWarps) {
+    // ------------------------------ producer: one lane feeds the ring ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int k = 0; k < a.K; ++k) {
+        for (int r = ra; r <= rb; ++r) {
+          for (int c = ca; c <= cb; ++c) {
+            const int t = r * g.nx + c;
+            const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+            if (slot < 0) continue;
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
+            const int i0 = Y0 - r * g.Sy, j0 = X0 - c * g.Sx;  // block origin inside the tile
+#pragma unroll
+            for (int va = 0; va < NV; ++va) {
+              const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
+              int sr0, sc0;
+              if (gc & V_T) {
+                sr0 = (gc & V_FI) ? g.Th - j0 - BS : j0;
+                sc0 = (gc & V_FJ) ? g.Tw - i0 - BS : i0;
+              } else {
+                sr0 = (gc & V_FI) ? g.Th - i0 - BS : i0;
+                sc0 = (gc & V_FJ) ? g.Tw - j0 - BS : j0;
+              }
+              const long long plane_row = (((long long)va * g.n_slots + slot) * a.K + k) * g.Th;
+              tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &tmap, &full[s], sc0, (int)(plane_row + sr0));
+            }
+            ++it;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------ consumers ------------------------------
+  // lane -> (row & 7, column & 3) so that swizzled row-wise reads hit 32 distinct banks
+  const int li = 8 * (warp & 3) + (lane >> 2);
+  const int ljb = 16 * (warp >> 2) + (lane & 3);  // columns ljb + 4e, e = 0..3
+  const int y = Y0 + li;
+  const bool y_ok = (y >= a.y0 && y < a.y1);
+  const int rows = a.y1 - a.y0;
+
+  // per-view shared-memory offsets of this thread's 4 pixels (loop invariant)
+  int off[NV][4];
+#pragma unroll
+  for (int va = 0; va < NV; ++va) {
+    const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int lj = ljb + 4 * e;
+      int rr, cc;
+      if (gc & V_T) {
+        rr = (gc & V_FI) ? BS - 1 - lj : lj;
+        cc = (gc & V_FJ) ? BS - 1 - li : li;
+      } else {
+        rr = (gc & V_FI) ? BS - 1 - li : li;
+        cc = (gc & V_FJ) ? BS - 1 - lj : lj;
+      }
+      off[va][e] = va * kBoxFloats + swz(rr, cc);
+    }
+  }
+
+  int it = 0;
+  for (int k = 0; k < a.K; ++k) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.init_num && y_ok) {
+      const size_t o = (size_t)(y - a.y0) * a.Wp + X0 + ljb;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[e] = a.init_num[(size_t)k * rows * a.Wp + o + 4 * e];
+        den[e] = a.init_den[o + 4 * e];
+      }
+    }
+    for (int r = ra; r <= rb; ++r) {
+      for (int c = ca; c <= cb; ++c) {
+        const int t = r * g.nx + c;
+        const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+        if (slot < 0) continue;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        const float* st = boxes + (size_t)s * NV * kBoxFloats;
+        float v[4];
+#pragma unroll
+        for (int va = 0; va < NV; ++va) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = red_pre<float>(a.red, st[off[va][e]]);
+            v[e] = (va == 0) ? pv : add_rn(v[e], pv);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+        const int ti = Y0 - r * g.Sy + li, tj = X0 - c * g.Sx + ljb;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float w = weight_at<float>(a.w, ti, tj + 4 * e);
+          acc[e] = add_rn(acc[e], mul_rn(red_post<float>(a.red, v[e], NV), w));
+          den[e] = add_rn(den[e], w);
+        }
+        ++it;
+      }
+    }
+    if (!y_ok) continue;
+    if (a.raw) {
+      const size_t o = (size_t)(y - a.y0) * a.Wp + X0 + ljb;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a.out_num[(size_t)k * rows * a.Wp + o + 4 * e] = acc[e];
+        if (k == 0) a.out_den[o + 4 * e] = den[e];
+      }
+    } else {
+      const int oi = y - a.top;
+      if (oi >= 0 && oi < a.H) {
+        float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int oj = X0 + ljb + 4 * e - a.left;
+          if (oj >= 0 && oj < a.W) o[oj] = acc[e] / den[e];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 8. stand-in model (bench / tests only): y[b,k,i,j] = sum_c Wm[k,c] x[b,c,i,j] + 0.01 (i - 2j + 7k)/T
 // ------------------------------------------------------------------------------------------------
@@ -719,6 +979,12 @@ __global__ void __launch_bounds__(kThreads) standin_model_kernel(StandinArgs a) 
   }
 }
 
+// TB200_FORCE_GENERIC_MERGE=1 routes tb_merge_all through the non-TMA kernel (used by tests to cross-check both).
+static inline bool tb_force_generic_merge() {
+  const char* v = getenv("TB200_FORCE_GENERIC_MERGE");
+  return v && v[0] == '1';
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace tb
@@ -740,6 +1006,47 @@ using namespace tb;
 // ================================================================================================
 // C-ABI entry points
 // ================================================================================================
+
+static PFN_cuTensorMapEncodeTiled get_tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// pred viewed as a 2-D fp32 tensor [rows, Tw]; box = 32 x 32, 128-byte swizzle
+static bool make_pred_tensor_map(const float* pred, unsigned long long rows, int Tw, CUtensorMap* map) {
+  PFN_cuTensorMapEncodeTiled enc = get_tensor_map_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)Tw, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Tw * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pred), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int TTA>
+static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const CUtensorMap& map, unsigned blocks, cudaStream_t s) {
+  constexpr int NV = Views<TTA>::count;
+  const size_t smem = tma_smem_bytes(NV);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  merge_all_tma_kernel<TTA><<<blocks, kTmaThreads, smem, s>>>(a, map);
+  return cudaGetLastError();
+}
+
 extern "C" {
 
 int tb_tta_views(int tta) {
@@ -800,10 +1107,13 @@ int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, i
   const long long blocks = (long long)n * a.nbx * a.nby;
   TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_slice_augment: grid too large");
   const bool vec = (Th % 4 == 0) && (Tw % 4 == 0) && aligned16(out);
+  const bool fast = (Th % BS == 0) && (Tw % BS == 0) && aligned16(out);
   cudaStream_t s = (cudaStream_t)stream;
 #define TB_SLICE(SrcT)                                                                   \
   do {                                                                                   \
-    if (vec)                                                                             \
+    if (fast) {                                                                          \
+      TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a)); \
+    } else if (vec)                                                                      \
       slice_augment_kernel<SrcT, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);         \
     else                                                                                 \
       slice_augment_kernel<SrcT, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);        \
@@ -1053,6 +1363,19 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
                       (grid->Sy % 4 == 0) && aligned16(out_num) &&
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
+  // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
+  const bool tma_ok = al && pred && (grid->Th % BS == 0) && (grid->Tw % BS == 0) && (grid->Sx % BS == 0) &&
+                      (grid->Sy % BS == 0) && !tb_force_generic_merge();
+  if (tma_ok) {
+    CUtensorMap map;
+    const unsigned long long rows = (unsigned long long)a.views.count * grid->n_slots * K * grid->Th;
+    if (rows < (1ull << 31) && make_pred_tensor_map(pred, rows, grid->Tw, &map)) {
+      cudaError_t e = cudaErrorInvalidValue;
+      TB_DISPATCH_TTA(tta, e = launch_merge_all_tma<TTA_>(a, map, (unsigned)blocks, s));
+      if (e != cudaSuccess) return cuda_fail(e, "merge_all_tma_kernel");
+      return TB_OK;
+    }
+  }
   if (al || al_tbl) {
     TB_DISPATCH_TTA(tta, merge_all_kernel<true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
   } else {

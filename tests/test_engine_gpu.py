@@ -179,3 +179,19 @@ def test_full_size_properties_cfg2():
     a = eng1.slice(dev, 100, 104)
     sums = a.view(8, 4, -1).double().sum(-1)
     assert torch.equal(sums, sums[0:1].expand(8, 4))
+
+
+def test_tma_and_generic_merge_kernels_agree_bitwise():
+    """tb_merge_all has two implementations (TMA-pipelined and plain-load); same arithmetic, same bits."""
+    import os
+
+    for tta_name, K in (("d4", 4), ("flips", 2), (None, 3), ("d2", 1)):
+        eng = TiledInferenceEngine((700, 900, 3), 128, 64, channels=K, weight="pyramid", tta=tta_name)
+        pred = torch.randn(eng.views * eng.num_tiles, K, 128, 128, generator=torch.Generator().manual_seed(5)).cuda()
+        fast = eng.merge(pred)
+        os.environ["TB200_FORCE_GENERIC_MERGE"] = "1"
+        try:
+            slow = eng.merge(pred)
+        finally:
+            del os.environ["TB200_FORCE_GENERIC_MERGE"]
+        assert torch.equal(fast, slow), tta_name

