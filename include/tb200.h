@@ -246,7 +246,8 @@ TB_API size_t tb_loss_workspace_bytes(int64_t B, int C, int64_t inner);
 /* Sigmoid (binary) focal loss. Replaces focal_loss_with_logits (losses/functional.py:19-107) and the
  * one-hot expansion of BinaryFocalLoss (losses/focal.py:77-105) when t_kind = TB_T_LABELS_I64.
  *   x f32 [B,C,inner]; t f32 [B,C,inner] or i64 [B,inner]; class_w NULL or f32 [C]
- *   loss_out: f32 scalar (MEAN/SUM), [C,inner] (BATCHWISE) or [B,C,inner] (NONE)
+ *   loss_out: f32 scalar (MEAN/SUM), [B,C,inner] (NONE), or for BATCHWISE a buffer of (B+1)*C*inner floats: the
+ *             first C*inner receive the result, the rest is scratch for the element losses
  *   grad: NULL or f32 [B,C,inner] = d(sum-reduced or mean-reduced scalar)/dx; for NONE/BATCHWISE it is the
  *         per-element derivative d loss_e / d x_e (diagonal), not available with normalized
  */
@@ -256,7 +257,7 @@ TB_API int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B
 
 /* Softmax focal loss. Replaces softmax_focal_loss_with_logits (losses/functional.py:110-173).
  *   x f32 [B,C,inner]; t i64 [B,inner]; ignore_index (int64) always active (default -100)
- *   loss_out: scalar (MEAN/SUM), [inner] (BATCHWISE), [B,inner] (NONE) */
+ *   loss_out: scalar (MEAN/SUM), [B,inner] (NONE), or for BATCHWISE (B+1)*inner floats (result first, scratch after) */
 TB_API int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C, int64_t inner, float gamma,
                              float reduced_threshold, int has_reduced_threshold, int64_t ignore_index,
                              int normalized, float eps, int reduction, const float* class_w, float* loss_out,
@@ -289,6 +290,10 @@ TB_API int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t 
  * grad = d loss / d x (NULL to skip); target gets no gradient here (shim negates for it). */
 TB_API int tb_wing_fwd_bwd(const float* x, const float* t, int64_t n, float width, float curvature, int reduction,
                     float* loss_out, float* grad, void* ws, size_t ws_bytes, void* stream);
+
+/* data[i] *= *scale_dev for i < n, skipped entirely when *scale_dev == 1.0f: lets autograd apply the upstream
+ * gradient (a device scalar) to a stored gradient buffer without a host synchronisation. */
+TB_API int tb_scale_by_device_scalar(float* data, int64_t n, const float* scale_dev, void* stream);
 
 /* Lovasz: given errors already sorted descending with their ground-truth bits (gt_sorted f32 0/1) for
  * `segs` independent segments (offsets int64 [segs+1]), compute per segment loss = dot(relu?(err), lovasz_grad)

@@ -779,9 +779,37 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // 7b. TMA-pipelined output-stationary merge (requires Th, Tw, Sx, Sy multiples of 32 and a single pred tensor)
+//
+// Persistent CTAs: each CTA walks canvas blocks blockIdx.x, blockIdx.x + gridDim.x, ... and the stage ring
+// keeps running across block boundaries, so the producer lane is always STAGES stages ahead of the
+// consumers (no pipeline fill/drain per block).
 // ------------------------------------------------------------------------------------------------
-template <int TTA>
-__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ CUtensorMap tmap) {
+struct BlockWork {
+  int Y0, X0, ra, rb, ca, cb;
+};
+
+__device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) {
+  const tb_grid& g = a.grid;
+  BlockWork w;
+  const int by = blk / a.nbx, bxi = blk - by * a.nbx;
+  w.Y0 = a.y0 - (a.y0 % BS) + by * BS;
+  w.X0 = (a.bx0 + bxi) * BS;
+  int ra = (w.Y0 - g.Th + g.Sy) / g.Sy;
+  if (w.Y0 - g.Th + 1 <= 0) ra = 0;
+  int rb = (w.Y0 + BS - 1) / g.Sy;
+  w.ra = max(ra, a.r0);
+  w.rb = min(rb, min(g.ny, a.r1) - 1);
+  int ca = (w.X0 - g.Tw + g.Sx) / g.Sx;
+  if (w.X0 - g.Tw + 1 <= 0) ca = 0;
+  w.ca = ca;
+  w.cb = min((w.X0 + BS - 1) / g.Sx, g.nx - 1);
+  return w;
+}
+
+// LINEAR: the reduction is MEAN or SUM (no per-element transform): keeps the switch out of the inner loop
+template <int TTA, bool LINEAR>
+__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                      int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
   constexpr int STAGES = tma_stages(NV);
@@ -792,9 +820,6 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
   uint64_t* empty = full + STAGES;
 
   const tb_grid& g = a.grid;
-  const int by = blockIdx.x / a.nbx, bxi = blockIdx.x - by * a.nbx;
-  const int Y0 = a.y0 - (a.y0 % BS) + by * BS;
-  const int X0 = (a.bx0 + bxi) * BS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -806,46 +831,39 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
   }
   __syncthreads();
 
-  // covering tiles (every 32x32 canvas block lies fully inside each tile that touches it)
-  int ra = (Y0 - g.Th + g.Sy) / g.Sy;
-  if (Y0 - g.Th + 1 <= 0) ra = 0;
-  int rb = (Y0 + BS - 1) / g.Sy;
-  ra = max(ra, a.r0);
-  rb = min(rb, min(g.ny, a.r1) - 1);
-  int ca = (X0 - g.Tw + g.Sx) / g.Sx;
-  if (X0 - g.Tw + 1 <= 0) ca = 0;
-  const int cb = min((X0 + BS - 1) / g.Sx, g.nx - 1);
-
   if (warp == kTmaConsumerWarps) {
     // ------------------------------ producer: one lane feeds the ring ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int k = 0; k < a.K; ++k) {
-        for (int r = ra; r <= rb; ++r) {
-          for (int c = ca; c <= cb; ++c) {
-            const int t = r * g.nx + c;
-            const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
-            if (slot < 0) continue;
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
-            const int i0 = Y0 - r * g.Sy, j0 = X0 - c * g.Sx;  // block origin inside the tile
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const BlockWork w = block_work(a, blk);
+        for (int k = 0; k < a.K; ++k) {
+          for (int r = w.ra; r <= w.rb; ++r) {
+            for (int c = w.ca; c <= w.cb; ++c) {
+              const int t = r * g.nx + c;
+              const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+              if (slot < 0) continue;
+              const int s = it % STAGES;
+              const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+              mbar_wait(&empty[s], ph ^ 1u);
+              mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
+              const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
 #pragma unroll
-            for (int va = 0; va < NV; ++va) {
-              const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
-              int sr0, sc0;
-              if (gc & V_T) {
-                sr0 = (gc & V_FI) ? g.Th - j0 - BS : j0;
-                sc0 = (gc & V_FJ) ? g.Tw - i0 - BS : i0;
-              } else {
-                sr0 = (gc & V_FI) ? g.Th - i0 - BS : i0;
-                sc0 = (gc & V_FJ) ? g.Tw - j0 - BS : j0;
+              for (int va = 0; va < NV; ++va) {
+                const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
+                int sr0, sc0;
+                if (gc & V_T) {
+                  sr0 = (gc & V_FI) ? g.Th - j0 - BS : j0;
+                  sc0 = (gc & V_FJ) ? g.Tw - i0 - BS : i0;
+                } else {
+                  sr0 = (gc & V_FI) ? g.Th - i0 - BS : i0;
+                  sc0 = (gc & V_FJ) ? g.Tw - j0 - BS : j0;
+                }
+                const long long plane_row = (((long long)va * g.n_slots + slot) * a.K + k) * g.Th;
+                tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &tmap, &full[s], sc0, (int)(plane_row + sr0));
               }
-              const long long plane_row = (((long long)va * g.n_slots + slot) * a.K + k) * g.Th;
-              tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &tmap, &full[s], sc0, (int)(plane_row + sr0));
+              ++it;
             }
-            ++it;
           }
         }
       }
@@ -854,90 +872,127 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
   }
 
   // ------------------------------ consumers ------------------------------
-  // lane -> (row & 7, column & 3) so that swizzled row-wise reads hit 32 distinct banks
-  const int li = 8 * (warp & 3) + (lane >> 2);
-  const int ljb = 16 * (warp >> 2) + (lane & 3);  // columns ljb + 4e, e = 0..3
-  const int y = Y0 + li;
-  const bool y_ok = (y >= a.y0 && y < a.y1);
+  // Each thread owns 4 consecutive columns (one 16-byte chunk) of one row of the 32x32 block:
+  //   row  li = 8*(warp&3) + (lane&7),  chunk cq = 4*(warp>>2) + (lane>>3)  (columns 4*cq .. 4*cq+3).
+  // A quarter-warp therefore touches 8 rows with distinct (row & 7): with the 128-byte swizzle its eight
+  // 16-byte chunks land in 8 distinct bank groups, so the LDS.128 of non-transposing views are conflict-free.
+  const int li = 8 * (warp & 3) + (lane & 7);
+  const int cq = 4 * (warp >> 2) + (lane >> 3);
+  const int lj = 4 * cq;
   const int rows = a.y1 - a.y0;
 
-  // per-view shared-memory offsets of this thread's 4 pixels (loop invariant)
-  int off[NV][4];
+  // loop-invariant shared-memory offsets: non-transposing views read one float4 (reversed when flipped along
+  // columns); transposing views read 4 scalars down a column
+  int off_vec[NV];      // float index of the float4 (non-transposing views)
+  int off_col[NV][4];   // float indices (transposing views)
 #pragma unroll
   for (int va = 0; va < NV; ++va) {
     const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
+    if (gc & V_T) {
+      const int cc = (gc & V_FJ) ? BS - 1 - li : li;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int lj = ljb + 4 * e;
-      int rr, cc;
-      if (gc & V_T) {
-        rr = (gc & V_FI) ? BS - 1 - lj : lj;
-        cc = (gc & V_FJ) ? BS - 1 - li : li;
-      } else {
-        rr = (gc & V_FI) ? BS - 1 - li : li;
-        cc = (gc & V_FJ) ? BS - 1 - lj : lj;
+      for (int e = 0; e < 4; ++e) {
+        const int rr = (gc & V_FI) ? BS - 1 - (lj + e) : lj + e;
+        off_col[va][e] = va * kBoxFloats + swz(rr, cc);
       }
-      off[va][e] = va * kBoxFloats + swz(rr, cc);
+      off_vec[va] = 0;
+    } else {
+      const int rr = (gc & V_FI) ? BS - 1 - li : li;
+      const int chunk = (gc & V_FJ) ? 7 - cq : cq;
+      off_vec[va] = va * kBoxFloats + rr * 32 + ((chunk ^ (rr & 7)) << 2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) off_col[va][e] = 0;
     }
   }
 
   int it = 0;
-  for (int k = 0; k < a.K; ++k) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.init_num && y_ok) {
-      const size_t o = (size_t)(y - a.y0) * a.Wp + X0 + ljb;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[e] = a.init_num[(size_t)k * rows * a.Wp + o + 4 * e];
-        den[e] = a.init_den[o + 4 * e];
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const BlockWork w = block_work(a, blk);
+    const int y = w.Y0 + li;
+    const bool y_ok = (y >= a.y0 && y < a.y1);
+    for (int k = 0; k < a.K; ++k) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.init_num && y_ok) {
+        const size_t o = (size_t)(y - a.y0) * a.Wp + w.X0 + lj;
+        const float4 n4 = *reinterpret_cast<const float4*>(a.init_num + (size_t)k * rows * a.Wp + o);
+        const float4 d4 = *reinterpret_cast<const float4*>(a.init_den + o);
+        acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
+        den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
-    }
-    for (int r = ra; r <= rb; ++r) {
-      for (int c = ca; c <= cb; ++c) {
-        const int t = r * g.nx + c;
-        const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
-        if (slot < 0) continue;
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        const float* st = boxes + (size_t)s * NV * kBoxFloats;
-        float v[4];
+      for (int r = w.ra; r <= w.rb; ++r) {
+        for (int c = w.ca; c <= w.cb; ++c) {
+          const int t = r * g.nx + c;
+          const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+          if (slot < 0) continue;
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          // weights first: their latency overlaps the wait for the stage
+          const int ti = w.Y0 - r * g.Sy + li, tj = w.X0 - c * g.Sx + lj;
+          float wt[4];
+          if (a.w.kind == TB_W_TABLE) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)ti * g.Tw + tj));
+            wt[0] = w4.x; wt[1] = w4.y; wt[2] = w4.z; wt[3] = w4.w;
+          } else {
 #pragma unroll
-        for (int va = 0; va < NV; ++va) {
+            for (int e = 0; e < 4; ++e) wt[e] = weight_at<float>(a.w, ti, tj + e);
+          }
+          mbar_wait(&full[s], ph);
+          const float* st = boxes + (size_t)s * NV * kBoxFloats;
+          float v[4];
+#pragma unroll
+          for (int va = 0; va < NV; ++va) {
+            const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
+            float q[4];
+            if (gc & V_T) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) q[e] = st[off_col[va][e]];
+            } else {
+              const float4 f = *reinterpret_cast<const float4*>(st + off_vec[va]);
+              if (gc & V_FJ) {
+                q[0] = f.w; q[1] = f.z; q[2] = f.y; q[3] = f.x;
+              } else {
+                q[0] = f.x; q[1] = f.y; q[2] = f.z; q[3] = f.w;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float pv = LINEAR ? q[e] : red_pre<float>(a.red, q[e]);
+              v[e] = (va == 0) ? pv : add_rn(v[e], pv);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float pv = red_pre<float>(a.red, st[off[va][e]]);
-            v[e] = (va == 0) ? pv : add_rn(v[e], pv);
+            float r4;
+            if (LINEAR)
+              r4 = (a.red == TB_RED_MEAN) ? v[e] / (float)NV : v[e];
+            else
+              r4 = red_post<float>(a.red, v[e], NV);
+            acc[e] = add_rn(acc[e], mul_rn(r4, wt[e]));
+            den[e] = add_rn(den[e], wt[e]);
           }
+          ++it;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
-        const int ti = Y0 - r * g.Sy + li, tj = X0 - c * g.Sx + ljb;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float w = weight_at<float>(a.w, ti, tj + 4 * e);
-          acc[e] = add_rn(acc[e], mul_rn(red_post<float>(a.red, v[e], NV), w));
-          den[e] = add_rn(den[e], w);
-        }
-        ++it;
       }
-    }
-    if (!y_ok) continue;
-    if (a.raw) {
-      const size_t o = (size_t)(y - a.y0) * a.Wp + X0 + ljb;
+      if (!y_ok) continue;
+      if (a.raw) {
+        const size_t o = (size_t)(y - a.y0) * a.Wp + w.X0 + lj;
+        *reinterpret_cast<float4*>(a.out_num + (size_t)k * rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (k == 0) *reinterpret_cast<float4*>(a.out_den + o) = make_float4(den[0], den[1], den[2], den[3]);
+      } else {
+        const int oi = y - a.top;
+        if (oi >= 0 && oi < a.H) {
+          float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
+          const int oj = w.X0 + lj - a.left;
+          if (((a.left & 3) == 0) && ((a.W & 3) == 0) && oj >= 0 && oj + 3 < a.W) {
+            __stcs(reinterpret_cast<float4*>(o + oj),
+                   make_float4(acc[0] / den[0], acc[1] / den[1], acc[2] / den[2], acc[3] / den[3]));
+          } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        a.out_num[(size_t)k * rows * a.Wp + o + 4 * e] = acc[e];
-        if (k == 0) a.out_den[o + 4 * e] = den[e];
-      }
-    } else {
-      const int oi = y - a.top;
-      if (oi >= 0 && oi < a.H) {
-        float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int oj = X0 + ljb + 4 * e - a.left;
-          if (oj >= 0 && oj < a.W) o[oj] = acc[e] / den[e];
+            for (int e = 0; e < 4; ++e)
+              if (oj + e >= 0 && oj + e < a.W) o[oj + e] = acc[e] / den[e];
+          }
         }
       }
     }
@@ -1028,23 +1083,33 @@ static bool make_pred_tensor_map(const float* pred, unsigned long long rows, int
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pred), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int TTA>
-static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const CUtensorMap& map, unsigned blocks, cudaStream_t s) {
+template <int TTA, bool LINEAR>
+static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const CUtensorMap& map, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
   const size_t smem = tma_smem_bytes(NV);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR>, kTmaThreads, smem);
+    if (e != cudaSuccess) return e;
+    ctas_per_sm = n > 0 ? n : 1;
   }
-  merge_all_tma_kernel<TTA><<<blocks, kTmaThreads, smem, s>>>(a, map);
+  const int grid = std::min(nblocks, sm_count() * ctas_per_sm);  // persistent: one resident wave
+  merge_all_tma_kernel<TTA, LINEAR><<<grid, kTmaThreads, smem, s>>>(a, map, nblocks);
   return cudaGetLastError();
+}
+
+template <int TTA>
+static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const CUtensorMap& map, int nblocks, cudaStream_t s) {
+  if (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) return launch_merge_all_tma_impl<TTA, true>(a, map, nblocks, s);
+  return launch_merge_all_tma_impl<TTA, false>(a, map, nblocks, s);
 }
 
 extern "C" {
@@ -1365,13 +1430,14 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
   const bool tma_ok = al && pred && (grid->Th % BS == 0) && (grid->Tw % BS == 0) && (grid->Sx % BS == 0) &&
-                      (grid->Sy % BS == 0) && !tb_force_generic_merge();
+                      (grid->Sy % BS == 0) && (Wp % 4 == 0) && (!init_num || (aligned16(init_num) && aligned16(init_den))) &&
+                      (!raw || aligned16(out_den)) && !tb_force_generic_merge();
   if (tma_ok) {
     CUtensorMap map;
     const unsigned long long rows = (unsigned long long)a.views.count * grid->n_slots * K * grid->Th;
     if (rows < (1ull << 31) && make_pred_tensor_map(pred, rows, grid->Tw, &map)) {
       cudaError_t e = cudaErrorInvalidValue;
-      TB_DISPATCH_TTA(tta, e = launch_merge_all_tma<TTA_>(a, map, (unsigned)blocks, s));
+      TB_DISPATCH_TTA(tta, e = launch_merge_all_tma<TTA_>(a, map, (int)blocks, s));
       if (e != cudaSuccess) return cuda_fail(e, "merge_all_tma_kernel");
       return TB_OK;
     }

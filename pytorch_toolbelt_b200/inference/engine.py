@@ -190,9 +190,10 @@ class TiledInferenceEngine:
         grid = self._grid(self.num_tiles)
         keep = []
         if torch.is_tensor(preds):
-            p = preds
-            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
-                raise ValueError("preds must be a contiguous float32 CUDA tensor")
+            if not preds.is_cuda:
+                raise ValueError("preds must live on the GPU")
+            p = preds.to(torch.float32).contiguous()  # no-ops for the expected layout
+            keep.append(p)
             if tuple(p.shape[1:]) != (k, th, tw) or p.shape[0] % self.views != 0:
                 raise ValueError(f"preds must be [A*n,{k},{th},{tw}], got {tuple(p.shape)}")
             n_slots = p.shape[0] // self.views
@@ -214,8 +215,10 @@ class TiledInferenceEngine:
             plane_set = k * th * tw
             device = preds[0].device
             for batch in preds:
-                if batch.dtype != torch.float32 or not batch.is_contiguous() or not batch.is_cuda:
-                    raise ValueError("every prediction batch must be a contiguous float32 CUDA tensor")
+                if not batch.is_cuda:
+                    raise ValueError("every prediction batch must live on the GPU")
+                batch = batch.to(torch.float32).contiguous()
+                keep.append(batch)
                 if tuple(batch.shape[1:]) != (k, th, tw) or batch.shape[0] % self.views != 0:
                     raise ValueError(f"prediction batches must be [A*b,{k},{th},{tw}], got {tuple(batch.shape)}")
                 b = batch.shape[0] // self.views

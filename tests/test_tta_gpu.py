@@ -70,7 +70,7 @@ def test_d4_vs_oracle_seeded(shape):
     y = torch.randn((8 * shape[0], 4) + shape[2:], generator=g)
     for red in ("mean", "sum"):
         ours, ref = tta.d4_image_deaugment(y.cuda(), reduction=red).cpu(), AO.deaugment(y, "d4", red)
-        if shape[2] >= 64:
+        if shape[2] % 32 == 0:
             assert torch.equal(ours, ref)  # same sequential view-order sum as torch CPU
         else:
             torch.testing.assert_close(ours, ref, rtol=1e-6, atol=1e-6)  # torch CPU re-associates tiny planes
