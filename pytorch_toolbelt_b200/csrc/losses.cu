@@ -492,11 +492,15 @@ __global__ void __launch_bounds__(kLT) region_stats_mc_kernel(RegionArgs a) {
   const long long npix = a.B * a.inner;
   const long long* labels = static_cast<const long long*>(a.t);
   // per-thread register accumulators for the first 8 classes (the common case), shared atomics beyond
-  for (long long pix = (long long)blockIdx.x * kLT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kLT) {
+  // uniform trip count: the warp shuffles below need every lane of the warp in the loop
+  for (long long base = (long long)blockIdx.x * kLT; base < npix; base += (long long)gridDim.x * kLT) {
+    const long long pix_raw = base + threadIdx.x;
+    const bool in_range = pix_raw < npix;
+    const long long pix = in_range ? pix_raw : npix - 1;
     const long long b = pix / a.inner, pos = pix - b * a.inner;
     const float* xp = a.x + b * a.C * a.inner + pos;
     const long long lab = __ldg(labels + pix);
-    const bool valid = !(a.p.has_ignore && (float)lab == a.p.ignore_index);
+    const bool valid = in_range && !(a.p.has_ignore && (float)lab == a.p.ignore_index);
     float mx = -INFINITY;
     if (a.p.from_logits) {
       for (int c = 0; c < a.C; ++c) mx = fmaxf(mx, __ldcs(xp + (long long)c * a.inner));
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kLT) region_stats_mc_kernel(RegionArgs a) {
       const float xc = __ldg(xp + (long long)c * a.inner);
       float pr = a.p.from_logits ? __expf(xc - mx) * inv_den : xc;
       float t = (valid && lab == c) ? 1.f : 0.f;
-      if (!valid) pr = 0.f;
+      if (!valid) pr = 0.f;  // ignored pixel (dice.py:93-96) or padding lane
       // warp-aggregate before touching shared memory
       float I = pr * t, S = pr + t, T = t;
 #pragma unroll

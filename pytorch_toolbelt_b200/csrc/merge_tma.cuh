@@ -42,6 +42,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Warp-level stage release: every lane's loaded values are consumed by the asm (so the loads have completed), the
+// warp converges, then one lane arrives.
+__device__ __forceinline__ void mbar_release_after(uint64_t* bar, float a, float b, float c, float d, bool elected) {
+  asm volatile("" ::"f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  __syncwarp();
+  if (elected) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   do {

@@ -672,6 +672,7 @@ struct MergeAllArgs {
   tb_grid grid;
   int K, red, Hp, Wp, y0, y1, r0, r1, raw, top, left, H, W;
   int bx0, nbx, nby;  // block-column offset and block counts covering the requested window
+  int debug;          // TB200_TMA_DEBUG bits (diagnostics only)
   ViewSet views;
   WeightDev<float> w;
   const float* init_num;
@@ -813,11 +814,14 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
   using V = Views<TTA>;
   constexpr int NV = V::count;
   constexpr int STAGES = tma_stages(NV);
-  extern __shared__ unsigned char smem_raw[];
-  // boxes must be 1024-byte aligned for the 128-byte swizzle atom
-  float* boxes = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(boxes + (size_t)STAGES * NV * kBoxFloats);
+  // Boxes must be 1024-byte aligned for the 128-byte swizzle atom. This kernel has no static shared memory, so
+  // the dynamic window starts at the (1024-aligned) base of the CTA's shared memory; checked below. No integer
+  // round trips on the pointers: the compiler must keep them in the shared address space (LDS, not generic LD).
+  extern __shared__ __align__(1024) float smem_boxes[];
+  float* boxes = smem_boxes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * NV * kBoxFloats);
   uint64_t* empty = full + STAGES;
+  if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
 
   const tb_grid& g = a.grid;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -843,9 +847,14 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
               const int t = r * g.nx + c;
               const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
               if (slot < 0) continue;
-              const int s = it % STAGES;
-              const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+              const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
+              const int s = it % ring;
+              const uint32_t ph = (uint32_t)(it / ring) & 1u;
               mbar_wait(&empty[s], ph ^ 1u);
+              // The consumers read this slot through the generic proxy; the TMA refill writes it through the
+              // async proxy. The mbarrier orders the threads, not the proxies: without this fence the refill can
+              // overtake reads that are still in flight (observed as a nondeterministic WAR race with 1-view stages).
+              fence_proxy_async();
               mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
               const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
 #pragma unroll
@@ -924,8 +933,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
           const int t = r * g.nx + c;
           const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
           if (slot < 0) continue;
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
+          const int s = it % ring;
+          const uint32_t ph = (uint32_t)(it / ring) & 1u;
           // weights first: their latency overlaps the wait for the stage
           const int ti = w.Y0 - r * g.Sy + li, tj = w.X0 - c * g.Sx + lj;
           float wt[4];
@@ -960,8 +970,10 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
               v[e] = (va == 0) ? pv : add_rn(v[e], pv);
             }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+          // Release the stage only after this warp's reads have RETURNED: the release is made data-dependent on
+          // the loaded values (a load still in flight when the producer's TMA refill lands would be a WAR race).
+          if (a.debug & 1) asm volatile("bar.sync 1, 256;" ::: "memory");  // all consumer warps done reading
+          mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float r4;
@@ -1413,6 +1425,10 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   a.pred = pred; a.grid = *grid; a.K = K; a.red = reduction; a.Hp = Hp; a.Wp = Wp;
   a.y0 = y0; a.y1 = y1; a.r0 = r0; a.r1 = r1; a.raw = raw; a.top = top; a.left = left; a.H = H; a.W = W;
   a.init_num = init_num; a.init_den = init_den; a.out_num = out_num; a.out_den = out_den;
+  {
+    const char* dbg = getenv("TB200_TMA_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   // block window: rows from floor(y0/BS) to ceil(y1/BS); columns cover the crop (or the whole canvas when raw)
   const int xa = raw ? 0 : left, xb = raw ? Wp : left + W;
   a.bx0 = xa / BS;

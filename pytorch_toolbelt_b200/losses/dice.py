@@ -68,7 +68,7 @@ class _RegionLoss(torch.autograd.Function):
         p = _params(cfg["jaccard"], mode, cfg["from_logits"], cfg["log_loss"], cfg["smooth"], cfg["eps"], cfg["ignore_index"])
         stats = torch.empty((c, 3), dtype=torch.float64, device=device)
         ws = K.workspace(b, c, inner, device)
-        want_grad = torch.is_grad_enabled() and y_pred.requires_grad
+        want_grad = ctx.needs_input_grad[0]
         grad = torch.empty((b, c, inner), dtype=torch.float32, device=device) if want_grad else None
         out = torch.empty((), dtype=torch.float32, device=device)
         classes = cfg["classes"]

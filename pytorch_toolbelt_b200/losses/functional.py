@@ -75,7 +75,7 @@ class _FocalLoss(_StoredGradLoss):
             t = target.detach().to(device=device, dtype=torch.float32).contiguous()
             t_kind = TB.T_DENSE_F32
         red = K.reduction_code(cfg["reduction"])
-        want_grad = _needs_grad(output)
+        want_grad = ctx.needs_input_grad[0]  # grad mode is off inside Function.forward: ask the ctx
         if cfg["normalized"] and red in (TB.LOSS_NONE, TB.LOSS_BATCHWISE) and want_grad:
             raise NotImplementedError("normalized focal loss with reduction none/batchwise_mean has no fused backward")
         p = N.FocalParams(
@@ -164,7 +164,7 @@ class _SoftmaxFocalLoss(_StoredGradLoss):
         if t.numel() != b * inner:
             raise ValueError(f"target must have shape [B,*] matching output [B,C,*]; got {tuple(target.shape)}")
         red = K.reduction_code(cfg["reduction"])
-        want_grad = _needs_grad(output)
+        want_grad = ctx.needs_input_grad[0]  # grad mode is off inside Function.forward: ask the ctx
         if cfg["normalized"] and red in (TB.LOSS_NONE, TB.LOSS_BATCHWISE) and want_grad:
             raise NotImplementedError("normalized focal loss with reduction none/batchwise_mean has no fused backward")
         if red == TB.LOSS_NONE:
@@ -266,7 +266,7 @@ class _WingLoss(_StoredGradLoss):
         if t.shape != x.shape:
             t = t.expand_as(x).contiguous()
         red = K.reduction_code(reduction) if reduction in ("mean", "sum") else TB.LOSS_NONE
-        want_grad = _needs_grad(output, target)
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         n = x.numel()
         out = torch.empty(x.shape if red == TB.LOSS_NONE else (), dtype=torch.float32, device=device)
         grad = torch.empty(x.shape, dtype=torch.float32, device=device) if want_grad else None

@@ -31,7 +31,7 @@ class _LovaszSortedDot(torch.autograd.Function):
         n = err_sorted.numel()
         device = errors.device
         loss = torch.empty(1, dtype=torch.float32, device=device)
-        want_grad = torch.is_grad_enabled() and errors.requires_grad
+        want_grad = ctx.needs_input_grad[0]
         grad_sorted = torch.empty(n, dtype=torch.float32, device=device) if want_grad else None
         ws = torch.empty(N.lib().tb_lovasz_workspace_bytes(n, 1), dtype=torch.uint8, device=device)
         offsets = (C.c_int64 * 2)(0, n)

@@ -113,7 +113,7 @@ def test_wing_and_lovasz_vs_golden(golden):
     check("lovasz_softmax_ignore", g, lambda z: L.LovaszLoss(ignore=255)(z, t_mc255), xkey="pr")
 
 
-def _cmp_oracle(ours_fn, oracle_fn, x, loss_rtol=1e-5, grad_rtol=1e-4):
+def _cmp_oracle(ours_fn, oracle_fn, x, loss_rtol=1e-5, grad_rtol=1e-4, grad_atol=None):
     xo = x.clone().requires_grad_(True)
     lo = oracle_fn(xo)
     lo.backward()
@@ -122,7 +122,8 @@ def _cmp_oracle(ours_fn, oracle_fn, x, loss_rtol=1e-5, grad_rtol=1e-4):
     lc.backward()
     np.testing.assert_allclose(lc.item(), lo.item(), rtol=loss_rtol)
     scale = xo.grad.abs().max().item()
-    np.testing.assert_allclose(xc.grad.cpu().numpy(), xo.grad.numpy(), rtol=grad_rtol, atol=2e-7 * scale + 1e-12)
+    atol = 2e-7 * scale + 1e-12 if grad_atol is None else grad_atol
+    np.testing.assert_allclose(xc.grad.cpu().numpy(), xo.grad.numpy(), rtol=grad_rtol, atol=atol)
 
 
 def test_losses_vs_oracle_seeded_large():
@@ -152,11 +153,14 @@ def test_losses_vs_oracle_seeded_large():
                 lambda z: LO.focal_sigmoid(z, t_ml, alpha=None) + LO.dice_loss(z, t_ml, "multilabel"), x)
     # upstream gradient other than 1 goes through the on-device scaling
     _cmp_oracle(lambda z: 0.37 * L.DiceLoss("multilabel")(z, t_ml.cuda()), lambda z: 0.37 * LO.dice_loss(z, t_ml, "multilabel"), x)
-    # lovasz: ties are unlikely with continuous inputs, compare with tolerance
+    # lovasz: every gradient entry is a DIFFERENCE of two O(1) float32 Jaccard values (lovasz.py:31-33), so the
+    # reference itself carries +-1 ulp(1.0) = 1.2e-7 of absolute noise per entry: compare with that atol
     lb = (torch.rand(B, H, W, generator=g) < 0.4).long()
-    _cmp_oracle(lambda z: L.BinaryLovaszLoss()(z, lb.cuda()), lambda z: LO.lovasz_hinge(z, lb), x[:, 0].contiguous(), grad_rtol=1e-3)
+    _cmp_oracle(lambda z: L.BinaryLovaszLoss()(z, lb.cuda()), lambda z: LO.lovasz_hinge(z, lb), x[:, 0].contiguous(),
+                grad_rtol=1e-3, grad_atol=3e-7)
     pr = torch.softmax(x, dim=1)
-    _cmp_oracle(lambda z: L.LovaszLoss()(z, t_mc.cuda()), lambda z: LO.lovasz_softmax(z, t_mc), pr, grad_rtol=1e-3)
+    _cmp_oracle(lambda z: L.LovaszLoss()(z, t_mc.cuda()), lambda z: LO.lovasz_softmax(z, t_mc), pr, grad_rtol=1e-3,
+                grad_atol=3e-7)
 
 
 def test_odd_shapes_and_many_classes():
@@ -203,19 +207,21 @@ def test_reference_known_answer_tests():
         yt = torch.tensor(yt).view(1, 1, 1, -1)
         assert float(crit(yp, yt)) == pytest.approx(want, abs=eps)
 
+    # reference tests/test_losses.py:160-209 (same vectors)
     crit = L.JaccardLoss(mode="multiclass", from_logits=False)
-    y_pred = torch.tensor([[[1, 0, 0, 1], [0, 1, 0, 0], [0, 0, 1, 0]]]).float()
-    assert float(crit(y_pred, torch.tensor([[0, 1, 2, 0]]))) == pytest.approx(0.0, abs=eps)
-    y_pred = torch.tensor([[[0, 0, 0, 0], [1, 0, 0, 1], [0, 1, 1, 0]]]).float()
-    assert float(crit(y_pred, torch.tensor([[0, 1, 2, 0]]))) == pytest.approx(1.0, abs=eps)
-    y_pred = torch.tensor([[[1, 0, 0, 1], [0, 0, 0, 0], [0, 1, 1, 0]]]).float()
-    assert float(crit(y_pred, torch.tensor([[0, 1, 2, 0]]))) == pytest.approx(1.0 - 1.0 / 3.0, abs=eps)
+    y_pred = torch.tensor([[[1.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 1.0]]])
+    assert float(crit(y_pred, torch.tensor([[0, 0, 1, 1]]))) == pytest.approx(0.0, abs=eps)
+    assert float(crit(y_pred, torch.tensor([[1, 1, 0, 0]]))) == pytest.approx(1.0, abs=eps)
+    y_pred = torch.tensor([[[1.0, 0.0, 1.0, 0.0], [0.0, 1.0, 0.0, 1.0]]])
+    assert float(crit(y_pred, torch.tensor([[1, 1, 0, 0]]))) == pytest.approx(1.0 - 1.0 / 3.0, abs=eps)
 
     crit = L.JaccardLoss(mode="multilabel", from_logits=False)
-    y_pred = torch.tensor([[[1, 1, 0, 0], [0, 0, 1, 1]]]).float()
-    assert float(crit(y_pred, torch.tensor([[[1, 1, 0, 0], [0, 0, 1, 1]]]))) == pytest.approx(0.0, abs=eps)
-    y_pred = torch.tensor([[[0, 0, 1, 1], [1, 1, 0, 0]]]).float()
-    assert float(crit(y_pred, torch.tensor([[[1, 1, 0, 0], [0, 0, 1, 1]]]))) == pytest.approx(1.0, abs=eps)
+    y_pred = torch.tensor([[[1.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 1.0]]])
+    assert float(crit(y_pred, y_pred.clone())) == pytest.approx(0.0, abs=eps)
+    assert float(crit(y_pred, 1 - y_pred)) == pytest.approx(1.0, abs=eps)
+    y_pred = torch.tensor([[[0.0, 1.0, 1.0, 0.0], [0.0, 1.0, 1.0, 0.0]]])
+    y_true = torch.tensor([[[1.0, 1.0, 0.0, 0.0], [1.0, 1.0, 0.0, 0.0]]])
+    assert float(crit(y_pred, y_true)) == pytest.approx(1.0 - 1.0 / 3.0, abs=eps)
 
     x = torch.randn((4, 3, 4, 4))
     y = torch.randint(0, 3, (4, 4, 4))
