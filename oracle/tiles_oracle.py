@@ -166,15 +166,15 @@ def merge_numpy_f64(tiles: Sequence[np.ndarray], grid: dict, weight: np.ndarray,
 class TorchMerger:
     """TileMerger, inference/tiles.py:290-350, on torch CPU (float32 by default): per tile `image += tile*w`."""
 
-    def __init__(self, canvas_hw, channels: int, weight: np.ndarray, dtype=torch.float32):
-        self.weight = torch.from_numpy(np.asarray(weight)[None]).to(dtype)
-        self.image = torch.zeros((channels, canvas_hw[0], canvas_hw[1]), dtype=dtype)
-        self.norm_mask = torch.zeros((1, canvas_hw[0], canvas_hw[1]), dtype=dtype)
+    def __init__(self, canvas_hw, channels: int, weight: np.ndarray, dtype=torch.float32, device="cpu"):
+        self.weight = torch.from_numpy(np.asarray(weight)[None]).to(device=device, dtype=dtype)
+        self.image = torch.zeros((channels, canvas_hw[0], canvas_hw[1]), dtype=dtype, device=device)
+        self.norm_mask = torch.zeros((1, canvas_hw[0], canvas_hw[1]), dtype=dtype, device=device)
 
     def integrate_batch(self, batch: torch.Tensor, coords):
         if len(batch) != len(coords):
             raise ValueError("Number of images in batch does not correspond to number of coordinates")
-        batch = batch.to(self.image.dtype)
+        batch = batch.to(device=self.image.device, dtype=self.image.dtype)
         for tile, c in zip(batch, coords):
             x, y, tw, th = (int(v) for v in c)
             self.image[:, y : y + th, x : x + tw] += tile * self.weight
