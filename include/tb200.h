@@ -217,6 +217,18 @@ TB_API int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, 
                  int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
                  int raw, int top, int left, int H, int W, float* out_num, float* out_den, void* stream);
 
+/* Same as tb_merge_all for predictions that arrive as the model's per-batch outputs (separate allocations):
+ * batch i is f32 [A*b_i, K, Th, Tw] (aug-major inside the batch) holding grid tiles
+ * [first_tile + i*batch_tiles, first_tile + i*batch_tiles + b_i), b_i = batch_tiles except b_last = last_batch_tiles.
+ * n_batches = 1 with first_tile = r0*nx is the "only this strip's tiles are resident" case of the multi-GPU path.
+ * Always takes the TMA-pipelined kernel (one rank-3 tensor map per batch in the kernel parameters, <= 192 batches);
+ * returns TB_ERR_UNSUPPORTED when the geometry is off the 32-pixel lattice (Th, Tw, Sx, Sy multiples of 32) so that
+ * the caller can fall back to tb_merge_all with a pointer table. batch_ptrs_host is a HOST array of device pointers. */
+TB_API int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
+                                int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                                int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
+                                int raw, int top, int left, int H, int W, float* out_num, float* out_den, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LOSSES  (forward value + gradient w.r.t. the logits in one call)
  * Layout for all of them: x is [B,C,inner] contiguous (inner = product of spatial dims).

@@ -133,6 +133,11 @@ SIGNATURES = {
         [_vp, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i,
          _vp, _vp, _vp],
     ),
+    "tb_merge_all_batched": (
+        _i,
+        [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
+         _i, _i, _vp, _vp, _vp],
+    ),
     "tb_loss_workspace_bytes": (_sz, [_i64, _i, _i64]),
     "tb_focal_fwd_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(FocalParams), _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb_softmax_focal_fwd_bwd": (

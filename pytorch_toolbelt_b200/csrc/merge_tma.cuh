@@ -63,14 +63,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// 2-D tiled TMA load: box (32 cols x 32 rows) at (col, row) -> shared memory, completion on `bar`.
-__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int col, int row) {
+// 3-D tiled TMA load: box (32 cols x 32 rows x 1 view) at (col, row, view) -> shared memory, completion on `bar`.
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, uint64_t* bar, int col, int row, int view) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(row)
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(row), "r"(view)
       : "memory");
 }
+
+// Tensor maps of the prediction tensors, passed by value in the kernel parameters (__grid_constant__). One map per
+// batch tensor [A*b, K, Th, Tw] viewed as the rank-3 tensor {Tw, b*K*Th, A} (view stride = b*K*Th*Tw elements).
+template <int MAXB>
+struct TmaMaps {
+  CUtensorMap m[MAXB];
+};
 
 // float index of element (rr, cc) inside a 128B-swizzled 32x32 fp32 box
 __device__ __forceinline__ int swz(int rr, int cc) { return rr * 32 + ((((cc >> 2) ^ (rr & 7)) << 2) | (cc & 3)); }

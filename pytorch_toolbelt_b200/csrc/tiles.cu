@@ -673,6 +673,8 @@ struct MergeAllArgs {
   int K, red, Hp, Wp, y0, y1, r0, r1, raw, top, left, H, W;
   int bx0, nbx, nby;  // block-column offset and block counts covering the requested window
   int debug;          // TB200_TMA_DEBUG bits (diagnostics only)
+  // TMA path: tile t (grid order) lives in batch tensor (t - first_tile) / batch_tiles at position (t - first_tile) % batch_tiles
+  int first_tile, batch_tiles, covered_tiles;
   ViewSet views;
   WeightDev<float> w;
   const float* init_num;
@@ -808,8 +810,8 @@ __device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) 
 }
 
 // LINEAR: the reduction is MEAN or SUM (no per-element transform): keeps the switch out of the inner loop
-template <int TTA, bool LINEAR>
-__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ CUtensorMap tmap,
+template <int TTA, bool LINEAR, int MAXB>
+__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
                                                                       int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
@@ -845,8 +847,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
           for (int r = w.ra; r <= w.rb; ++r) {
             for (int c = w.ca; c <= w.cb; ++c) {
               const int t = r * g.nx + c;
-              const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
-              if (slot < 0) continue;
+              const int rel = t - a.first_tile;
+              if (rel < 0 || rel >= a.covered_tiles) continue;  // tile not resident (band mode): uniform decision
+              const int bi = rel / a.batch_tiles, pos = rel - bi * a.batch_tiles;
               const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
               const int s = it % ring;
               const uint32_t ph = (uint32_t)(it / ring) & 1u;
@@ -868,8 +871,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
                   sr0 = (gc & V_FI) ? g.Th - i0 - BS : i0;
                   sc0 = (gc & V_FJ) ? g.Tw - j0 - BS : j0;
                 }
-                const long long plane_row = (((long long)va * g.n_slots + slot) * a.K + k) * g.Th;
-                tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &tmap, &full[s], sc0, (int)(plane_row + sr0));
+                const int row = (pos * a.K + k) * g.Th + sr0;
+                tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi], &full[s], sc0, row, va);
               }
               ++it;
             }
@@ -931,8 +934,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
       for (int r = w.ra; r <= w.rb; ++r) {
         for (int c = w.ca; c <= w.cb; ++c) {
           const int t = r * g.nx + c;
-          const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
-          if (slot < 0) continue;
+          const int rel = t - a.first_tile;
+          if (rel < 0 || rel >= a.covered_tiles) continue;
           const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
           const int s = it % ring;
           const uint32_t ph = (uint32_t)(it / ring) & 1u;
@@ -1086,42 +1089,55 @@ static PFN_cuTensorMapEncodeTiled get_tensor_map_encoder() {
   return fn;
 }
 
-// pred viewed as a 2-D fp32 tensor [rows, Tw]; box = 32 x 32, 128-byte swizzle
-static bool make_pred_tensor_map(const float* pred, unsigned long long rows, int Tw, CUtensorMap* map) {
+// One batch tensor [A*b, K, Th, Tw] as the rank-3 fp32 tensor {Tw, b*K*Th, A}; box = 32 x 32 x 1, 128-byte swizzle
+static bool make_pred_tensor_map(const float* base, int b, int K, int Th, int Tw, int A, CUtensorMap* map) {
   PFN_cuTensorMapEncodeTiled enc = get_tensor_map_encoder();
   if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)Tw, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Tw * sizeof(float)};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pred), dims, strides, box, estr,
+  const unsigned long long rows = (unsigned long long)b * K * Th;
+  if (rows >= (1ull << 31)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)Tw, (cuuint64_t)rows, (cuuint64_t)A};
+  cuuint64_t strides[2] = {(cuuint64_t)Tw * sizeof(float), (cuuint64_t)rows * Tw * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int TTA, bool LINEAR>
-static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const CUtensorMap& map, int nblocks, cudaStream_t s) {
+constexpr int kMaxTmaBatches = 192;  // 192 x 128 B of tensor maps = 24 KB of kernel parameters (limit 32 KB)
+
+template <int TTA, bool LINEAR, int MAXB>
+static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
   const size_t smem = tma_smem_bytes(NV);
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR>, kTmaThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR, MAXB>, kTmaThreads, smem);
     if (e != cudaSuccess) return e;
     ctas_per_sm = n > 0 ? n : 1;
   }
   const int grid = std::min(nblocks, sm_count() * ctas_per_sm);  // persistent: one resident wave
-  merge_all_tma_kernel<TTA, LINEAR><<<grid, kTmaThreads, smem, s>>>(a, map, nblocks);
+  merge_all_tma_kernel<TTA, LINEAR, MAXB><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
   return cudaGetLastError();
 }
 
-template <int TTA>
-static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const CUtensorMap& map, int nblocks, cudaStream_t s) {
-  if (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) return launch_merge_all_tma_impl<TTA, true>(a, map, nblocks, s);
-  return launch_merge_all_tma_impl<TTA, false>(a, map, nblocks, s);
+template <int TTA, int MAXB>
+static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
+  if (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) return launch_merge_all_tma_impl<TTA, true, MAXB>(a, maps, nblocks, s);
+  return launch_merge_all_tma_impl<TTA, false, MAXB>(a, maps, nblocks, s);
+}
+
+// Geometry test for the TMA path (everything on the 32-pixel lattice, 16-byte aligned side buffers).
+static bool tma_geometry_ok(const tb_grid* grid, int Wp, const float* init_num, const float* init_den, int raw,
+                            const float* out_num, const float* out_den, const tb_weight* weight) {
+  return (grid->Th % BS == 0) && (grid->Tw % BS == 0) && (grid->Sx % BS == 0) && (grid->Sy % BS == 0) && (Wp % 4 == 0) &&
+         aligned16(out_num) && (weight->kind != TB_W_TABLE || aligned16(weight->table)) &&
+         (!init_num || (aligned16(init_num) && aligned16(init_den))) && (!raw || aligned16(out_den)) &&
+         !tb_force_generic_merge();
 }
 
 extern "C" {
@@ -1445,15 +1461,14 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
-  const bool tma_ok = al && pred && (grid->Th % BS == 0) && (grid->Tw % BS == 0) && (grid->Sx % BS == 0) &&
-                      (grid->Sy % BS == 0) && (Wp % 4 == 0) && (!init_num || (aligned16(init_num) && aligned16(init_den))) &&
-                      (!raw || aligned16(out_den)) && !tb_force_generic_merge();
-  if (tma_ok) {
-    CUtensorMap map;
-    const unsigned long long rows = (unsigned long long)a.views.count * grid->n_slots * K * grid->Th;
-    if (rows < (1ull << 31) && make_pred_tensor_map(pred, rows, grid->Tw, &map)) {
+  if (al && pred && !grid->tile_slot && tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
+    TmaMaps<1> maps;
+    if (make_pred_tensor_map(pred, grid->n_slots, K, grid->Th, grid->Tw, a.views.count, &maps.m[0])) {
+      a.first_tile = 0;
+      a.batch_tiles = grid->n_slots;
+      a.covered_tiles = grid->n_slots;
       cudaError_t e = cudaErrorInvalidValue;
-      TB_DISPATCH_TTA(tta, e = launch_merge_all_tma<TTA_>(a, map, (int)blocks, s));
+      TB_DISPATCH_TTA(tta, e = (launch_merge_all_tma<TTA_, 1>(a, maps, (int)blocks, s)));
       if (e != cudaSuccess) return cuda_fail(e, "merge_all_tma_kernel");
       return TB_OK;
     }
@@ -1464,6 +1479,72 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
     TB_DISPATCH_TTA(tta, merge_all_kernel<false, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
   }
   TB_LAUNCH_CHECK("merge_all_kernel");
+  return TB_OK;
+}
+
+int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
+                         int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight, int Hp,
+                         int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw, int top,
+                         int left, int H, int W, float* out_num, float* out_den, void* stream) {
+  TB_REQUIRE(batch_ptrs_host && grid && weight && out_num, TB_ERR_ARG, "tb_merge_all_batched: null pointer");
+  TB_REQUIRE(n_batches > 0 && batch_tiles > 0 && last_batch_tiles > 0 && last_batch_tiles <= batch_tiles && first_tile >= 0,
+             TB_ERR_ARG, "tb_merge_all_batched: bad batch description");
+  TB_REQUIRE(K > 0 && grid->nx > 0 && grid->ny > 0 && grid->Sx > 0 && grid->Sy > 0 && grid->Th > 0 && grid->Tw > 0,
+             TB_ERR_ARG, "tb_merge_all_batched: bad grid");
+  const long long covered = (long long)(n_batches - 1) * batch_tiles + last_batch_tiles;
+  TB_REQUIRE(first_tile + covered <= (long long)grid->nx * grid->ny, TB_ERR_ARG, "tb_merge_all_batched: batches exceed the grid");
+  TB_REQUIRE(0 <= y0 && y0 < y1 && y1 <= Hp, TB_ERR_ARG, "tb_merge_all_batched: bad row window [%d,%d) of %d", y0, y1, Hp);
+  TB_REQUIRE(0 <= r0 && r0 <= r1 && r1 <= grid->ny, TB_ERR_ARG, "tb_merge_all_batched: bad tile-row window");
+  TB_REQUIRE((grid->nx - 1) * grid->Sx + grid->Tw <= Wp && (grid->ny - 1) * grid->Sy + grid->Th <= Hp, TB_ERR_ARG,
+             "tb_merge_all_batched: grid exceeds the canvas");
+  TB_REQUIRE(reduction >= TB_RED_MEAN && reduction <= TB_RED_LOG1P, TB_ERR_ARG, "tb_merge_all_batched: bad reduction %d", reduction);
+  TB_REQUIRE(!raw || out_den, TB_ERR_ARG, "tb_merge_all_batched: raw output needs out_den");
+  TB_REQUIRE((init_num == nullptr) == (init_den == nullptr), TB_ERR_ARG, "tb_merge_all_batched: init_num/init_den mismatch");
+  TB_REQUIRE(raw || (top >= 0 && left >= 0 && H > 0 && W > 0 && top + H <= Hp && left + W <= Wp), TB_ERR_ARG,
+             "tb_merge_all_batched: crop window outside the canvas");
+  MergeAllArgs a;
+  TB_REQUIRE(make_views(tta, &a.views), TB_ERR_ARG, "tb_merge_all_batched: unknown tta %d", tta);
+  TB_REQUIRE(!views_have_transpose(a.views) || grid->Th == grid->Tw, TB_ERR_ARG, "tb_merge_all_batched: D4 needs square tiles");
+  TB_REQUIRE(make_weight<float>(weight, grid->Th, grid->Tw, &a.w), TB_ERR_ARG, "tb_merge_all_batched: bad weight spec");
+  if (n_batches > kMaxTmaBatches || !tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight))
+    return fail(TB_ERR_UNSUPPORTED, "tb_merge_all_batched: geometry off the 32-pixel lattice or > %d batches; use tb_merge_all",
+                kMaxTmaBatches);
+  for (int i = 0; i < n_batches; ++i)
+    if (!batch_ptrs_host[i] || !aligned16(batch_ptrs_host[i]))
+      return fail(TB_ERR_ALIGN, "tb_merge_all_batched: batch %d pointer is null or not 16-byte aligned", i);
+  a.pred = nullptr; a.grid = *grid; a.K = K; a.red = reduction; a.Hp = Hp; a.Wp = Wp;
+  a.grid.tile_slot = nullptr; a.grid.tile_ptr = nullptr; a.grid.tile_vstride = nullptr;
+  a.y0 = y0; a.y1 = y1; a.r0 = r0; a.r1 = r1; a.raw = raw; a.top = top; a.left = left; a.H = H; a.W = W;
+  a.init_num = init_num; a.init_den = init_den; a.out_num = out_num; a.out_den = out_den;
+  {
+    const char* dbg = getenv("TB200_TMA_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
+  a.first_tile = first_tile; a.batch_tiles = batch_tiles; a.covered_tiles = (int)covered;
+  const int xa = raw ? 0 : left, xb = raw ? Wp : left + W;
+  a.bx0 = xa / BS;
+  a.nbx = (xb + BS - 1) / BS - a.bx0;
+  a.nby = (y1 + BS - 1) / BS - y0 / BS;
+  const long long blocks = (long long)a.nbx * a.nby;
+  TB_REQUIRE(blocks > 0 && blocks < (1ll << 31), TB_ERR_ARG, "tb_merge_all_batched: grid too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (n_batches == 1) {
+    TmaMaps<1> maps;
+    if (!make_pred_tensor_map(batch_ptrs_host[0], last_batch_tiles, K, grid->Th, grid->Tw, a.views.count, &maps.m[0]))
+      return fail(TB_ERR_UNSUPPORTED, "tb_merge_all_batched: cuTensorMapEncodeTiled failed");
+    a.batch_tiles = last_batch_tiles;
+    TB_DISPATCH_TTA(tta, e = (launch_merge_all_tma<TTA_, 1>(a, maps, (int)blocks, s)));
+  } else {
+    static thread_local TmaMaps<kMaxTmaBatches> maps;  // 24 KB: keep it off the stack
+    for (int i = 0; i < n_batches; ++i) {
+      const int b = (i == n_batches - 1) ? last_batch_tiles : batch_tiles;
+      if (!make_pred_tensor_map(batch_ptrs_host[i], b, K, grid->Th, grid->Tw, a.views.count, &maps.m[i]))
+        return fail(TB_ERR_UNSUPPORTED, "tb_merge_all_batched: cuTensorMapEncodeTiled failed for batch %d", i);
+    }
+    TB_DISPATCH_TTA(tta, e = (launch_merge_all_tma<TTA_, kMaxTmaBatches>(a, maps, (int)blocks, s)));
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "merge_all_tma_kernel(batched)");
   return TB_OK;
 }
 

@@ -175,8 +175,8 @@ class TiledInferenceEngine:
         """All predictions -> merged, normalised, cropped logits float32 [K,H,W].
 
         ``preds`` is either one tensor [A*N,K,Th,Tw] (aug-major over the whole grid) or the list of the model's
-        per-batch outputs ([A*b,K,Th,Tw] each, batches in grid order) -- the latter is merged in place through a
-        pointer table, without concatenating.
+        per-batch outputs ([A*b,K,Th,Tw] each, batches in grid order) -- the latter is merged in place (one TMA
+        tensor map per batch, or a device pointer table off the 32-pixel lattice), without concatenating.
 
         Band mode (multi-GPU strips): ``rows=(y0,y1)`` canvas rows to produce, ``tile_rows=(r0,r1)`` contributing
         tile rows, ``raw=True`` returns un-normalised ``(num [K,y1-y0,Wp], den [y1-y0,Wp])``, ``init`` seeds the
@@ -189,54 +189,49 @@ class TiledInferenceEngine:
         r0, r1 = tile_rows if tile_rows is not None else (0, ny)
         grid = self._grid(self.num_tiles)
         keep = []
+        plane_set = k * th * tw
         if torch.is_tensor(preds):
-            if not preds.is_cuda:
-                raise ValueError("preds must live on the GPU")
-            p = preds.to(torch.float32).contiguous()  # no-ops for the expected layout
-            keep.append(p)
-            if tuple(p.shape[1:]) != (k, th, tw) or p.shape[0] % self.views != 0:
-                raise ValueError(f"preds must be [A*n,{k},{th},{tw}], got {tuple(p.shape)}")
-            n_slots = p.shape[0] // self.views
-            if n_slots != self.num_tiles and tile_rows is None:
-                raise ValueError(f"preds holds {n_slots} tiles per view, the grid has {self.num_tiles}")
-            grid.n_slots = n_slots
-            if n_slots != self.num_tiles:
-                # band mode with only the band's tiles resident: slot = tile - r0*nx
-                slots = np.full(self.num_tiles, -1, dtype=np.int32)
-                slots[r0 * nx : r0 * nx + n_slots] = np.arange(n_slots, dtype=np.int32)
-                slot_dev = torch.from_numpy(slots).to(p.device)
-                keep.append(slot_dev)
-                grid.tile_slot = slot_dev.data_ptr()
-            pred_ptr, device = p.data_ptr(), p.device
+            preds = [preds]
+        batches = []
+        for batch in preds:
+            if not batch.is_cuda:
+                raise ValueError("predictions must live on the GPU")
+            batch = batch.to(torch.float32).contiguous()  # no-ops for the expected layout
+            if tuple(batch.shape[1:]) != (k, th, tw) or batch.shape[0] % self.views != 0:
+                raise ValueError(f"predictions must be [A*b,{k},{th},{tw}], got {tuple(batch.shape)}")
+            if batch.data_ptr() % 16 != 0:
+                raise ValueError("prediction tensors must be 16-byte aligned")
+            batches.append(batch)
+        keep += batches
+        sizes = [b.shape[0] // self.views for b in batches]
+        total = sum(sizes)
+        if total == self.num_tiles:
+            first_tile = 0  # the whole grid is resident; tile_rows (if any) only restricts who contributes
+        elif tile_rows is not None and total == (r1 - r0) * nx:
+            first_tile = r0 * nx  # only this strip's tiles are resident (multi-GPU)
         else:
+            raise ValueError(f"predictions cover {total} tiles; expected the whole grid ({self.num_tiles})"
+                             + (f" or the strip's {(r1 - r0) * nx}" if tile_rows is not None else ""))
+        device = batches[0].device
+        uniform = all(sz == sizes[0] for sz in sizes[:-1]) and sizes[-1] <= sizes[0]
+        whole_grid_single = len(batches) == 1 and sizes[0] == self.num_tiles
+        mode = "single" if whole_grid_single else ("batched" if uniform else "table")
+        pred_ptr = None
+        if mode == "single":
+            pred_ptr = batches[0].data_ptr()
+        elif mode == "table":
             ptrs = np.zeros(self.num_tiles, dtype=np.int64)
             vstr = np.zeros(self.num_tiles, dtype=np.int64)
-            t = r0 * nx if tile_rows is not None else 0
-            plane_set = k * th * tw
-            device = preds[0].device
-            for batch in preds:
-                if not batch.is_cuda:
-                    raise ValueError("every prediction batch must live on the GPU")
-                batch = batch.to(torch.float32).contiguous()
-                keep.append(batch)
-                if tuple(batch.shape[1:]) != (k, th, tw) or batch.shape[0] % self.views != 0:
-                    raise ValueError(f"prediction batches must be [A*b,{k},{th},{tw}], got {tuple(batch.shape)}")
-                b = batch.shape[0] // self.views
-                base = batch.data_ptr()
-                if base % 16 != 0:
-                    raise ValueError("prediction batches must be 16-byte aligned")
-                ptrs[t : t + b] = base + np.arange(b, dtype=np.int64) * (plane_set * 4)
+            t = first_tile
+            for batch, b in zip(batches, sizes):
+                ptrs[t : t + b] = batch.data_ptr() + np.arange(b, dtype=np.int64) * (plane_set * 4)
                 vstr[t : t + b] = b * plane_set
                 t += b
-            expected = (r1 * nx) if tile_rows is not None else self.num_tiles
-            if t != expected:
-                raise ValueError(f"prediction batches cover {t} tiles, expected {expected}")
             ptr_dev = torch.from_numpy(ptrs).to(device)
             vstr_dev = torch.from_numpy(vstr).to(device)
             keep += [ptr_dev, vstr_dev]
             grid.tile_ptr = ptr_dev.data_ptr()
             grid.tile_vstride = vstr_dev.data_ptr()
-            pred_ptr = None
         top, left = self.slicer.margin_top, self.slicer.margin_left
         h, w = self.slicer.image_height, self.slicer.image_width
         init_num = init_den = None
@@ -255,12 +250,29 @@ class TiledInferenceEngine:
             elif tuple(out.shape) != (k, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous float32 tensor [{k},{h},{w}]")
             out_num, out_den, result = out.data_ptr(), None, out
+        common = (k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1, N.ptr(init_num), N.ptr(init_den),
+                  1 if raw else 0, top, left, h, w, out_num, out_den, N.stream_ptr(device))
         with torch.cuda.device(device):
-            rc = N.lib().tb_merge_all(
-                pred_ptr, C.byref(grid), k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1,
-                N.ptr(init_num), N.ptr(init_den), 1 if raw else 0, top, left, h, w, out_num, out_den,
-                N.stream_ptr(device),
-            )
+            rc = None
+            if mode == "batched":
+                ptr_arr = (C.c_void_p * len(batches))(*[b.data_ptr() for b in batches])
+                rc = N.lib().tb_merge_all_batched(ptr_arr, len(batches), sizes[0], sizes[-1], first_tile, C.byref(grid), *common)
+                if rc == -2:  # TB_ERR_UNSUPPORTED: geometry off the TMA lattice -> pointer-table kernel
+                    rc = None
+                    ptrs = np.zeros(self.num_tiles, dtype=np.int64)
+                    vstr = np.zeros(self.num_tiles, dtype=np.int64)
+                    t = first_tile
+                    for batch, b in zip(batches, sizes):
+                        ptrs[t : t + b] = batch.data_ptr() + np.arange(b, dtype=np.int64) * (plane_set * 4)
+                        vstr[t : t + b] = b * plane_set
+                        t += b
+                    ptr_dev = torch.from_numpy(ptrs).to(device)
+                    vstr_dev = torch.from_numpy(vstr).to(device)
+                    keep += [ptr_dev, vstr_dev]
+                    grid.tile_ptr = ptr_dev.data_ptr()
+                    grid.tile_vstride = vstr_dev.data_ptr()
+            if rc is None:
+                rc = N.lib().tb_merge_all(pred_ptr, C.byref(grid), *common)
         N.check(rc, "tb_merge_all")
         # tables must outlive the asynchronous launch: park them until the next call on this engine
         self._keepalive = keep

@@ -195,3 +195,21 @@ def test_tma_and_generic_merge_kernels_agree_bitwise():
         finally:
             del os.environ["TB200_FORCE_GENERIC_MERGE"]
         assert torch.equal(fast, slow), tta_name
+
+
+def test_batched_prediction_lists_take_the_tma_path_and_agree():
+    """predict(batch_size=b): per-batch model outputs (separate allocations) merged through per-batch tensor maps."""
+    K = 3
+    eng = TiledInferenceEngine((900, 700, 3), 128, 64, channels=K, weight="pyramid", tta="d4")
+    A, n = eng.views, eng.num_tiles
+    pred = torch.randn(A, n, K, 128, 128, generator=torch.Generator().manual_seed(9)).cuda()
+    whole = eng.merge(pred.reshape(-1, K, 128, 128))
+    for bsz in (1, 7, 8, n):
+        batches = [pred[:, s : s + bsz].reshape(-1, K, 128, 128).contiguous() for s in range(0, n, bsz)]
+        assert torch.equal(eng.merge(batches), whole), bsz
+    # non-uniform batch sizes -> pointer-table kernel, same bits
+    cuts = [0, 5, 6, 20, n]
+    batches = [pred[:, a:b].reshape(-1, K, 128, 128).contiguous() for a, b in zip(cuts, cuts[1:])]
+    assert torch.equal(eng.merge(batches), whole)
+    with pytest.raises(ValueError):
+        eng.merge(batches[:-1])
