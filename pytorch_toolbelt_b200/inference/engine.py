@@ -294,3 +294,69 @@ class TiledInferenceEngine:
                 pred = pred.float()
             outputs.append(pred.contiguous())
         return self.merge(outputs[0] if len(outputs) == 1 else outputs)
+
+    # ------------------------------------------------------------------ host -> host, pipelined over tile rows
+    @torch.no_grad()
+    def predict_to_host(self, image_host: torch.Tensor, model: Callable[[torch.Tensor], torch.Tensor],
+                        out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 2, layout: str = "HWC") -> torch.Tensor:
+        """Pinned host image -> pinned host logits [K,H,W], software-pipelined over chunks of tile rows.
+
+        For every chunk: (copy stream A) upload the image rows the chunk needs; (compute stream) slice+augment, model,
+        merge the canvas rows that are now final (band mode of tb_merge_all_batched over the model outputs so far);
+        (copy stream B) download those output rows. PCIe transfers in both directions overlap the kernels; the
+        arithmetic and its order are identical to ``predict`` (bit-identical result).
+        """
+        if layout != "HWC":
+            raise ValueError("predict_to_host streams HWC images")
+        dev = self.device
+        k = self.channels
+        h, w = self.slicer.image_height, self.slicer.image_width
+        nx, ny, sw, sh, th, tw = self._grid_dims
+        hp, wp = self.slicer.target_shape
+        top = self.slicer.margin_top
+        if not image_host.is_pinned():
+            image_host = image_host.pin_memory()
+        if out_host is None:
+            out_host = torch.empty((k, h, w), dtype=torch.float32).pin_memory()
+        if not hasattr(self, "_pipe"):
+            self._pipe = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
+                              image=torch.empty(image_host.shape, dtype=image_host.dtype, device=dev),
+                              out=torch.empty((k, h, w), dtype=torch.float32, device=dev))
+        pipe = self._pipe
+        image_dev, out_dev = pipe["image"], pipe["out"]
+        if image_dev.shape != image_host.shape or image_dev.dtype != image_host.dtype:
+            image_dev = pipe["image"] = torch.empty(image_host.shape, dtype=image_host.dtype, device=dev)
+        main = torch.cuda.current_stream(dev)
+        pipe["h2d"].wait_stream(main)  # the previous call's kernels may still read image_dev
+        pipe["d2h"].wait_stream(main)
+        # border modes whose source rows can lie far from the tile (WRAP) need the whole image up front
+        stream_rows = self.border_type != 3
+        uploaded, merged_until = 0, 0
+        outputs: List[torch.Tensor] = []
+        for r in range(0, ny, rows_per_chunk):
+            rb = min(r + rows_per_chunk, ny)
+            need = h if (rb == ny or not stream_rows) else min(h, max(0, (rb - 1) * sh + th - top))
+            if need > uploaded:
+                with torch.cuda.stream(pipe["h2d"]):
+                    image_dev[uploaded:need].copy_(image_host[uploaded:need], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(pipe["h2d"])
+                main.wait_event(ev)
+                uploaded = need
+            x = self.slice(image_dev, r * nx, rb * nx)
+            y = model(x)
+            outputs.append(y if y.dtype == torch.float32 and y.is_contiguous() else y.float().contiguous())
+            y_cur = hp if rb == ny else rb * sh
+            self.merge(outputs, out=out_dev, rows=(merged_until, y_cur), tile_rows=(0, rb))
+            o0, o1 = max(merged_until - top, 0), min(y_cur - top, h)
+            if o1 > o0:
+                ev2 = torch.cuda.Event()
+                ev2.record(main)
+                pipe["d2h"].wait_event(ev2)
+                with torch.cuda.stream(pipe["d2h"]):
+                    for kk in range(k):  # per-channel row blocks are contiguous on both sides: truly async copies
+                        out_host[kk, o0:o1].copy_(out_dev[kk, o0:o1], non_blocking=True)
+            merged_until = y_cur
+        main.wait_stream(pipe["d2h"])
+        self._keepalive_outputs = outputs  # kernels of this call may still be reading them
+        return out_host

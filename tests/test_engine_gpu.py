@@ -213,3 +213,18 @@ def test_batched_prediction_lists_take_the_tma_path_and_agree():
     assert torch.equal(eng.merge(batches), whole)
     with pytest.raises(ValueError):
         eng.merge(batches[:-1])
+
+
+def test_predict_to_host_pipelined_is_bit_identical_to_predict():
+    rng = np.random.default_rng(6)
+    image = rng.integers(0, 256, (1000, 840, 3)).astype(np.uint8)
+    K = 4
+    Wm = OP.standin_model_weights(K, 3)
+    for border in (0, 4):
+        eng = TiledInferenceEngine(image.shape, 128, 64, channels=K, weight="pyramid", tta="d4", border_type=border)
+        ref = eng.predict(image, lambda x: standin_cuda(x, Wm), batch_size=None)
+        host_img = torch.from_numpy(image).pin_memory()
+        for rows in (1, 2, 5, 100):
+            out = eng.predict_to_host(host_img, lambda x: standin_cuda(x, Wm), rows_per_chunk=rows)
+            torch.cuda.synchronize()
+            assert out.is_pinned() and torch.equal(out, ref.cpu()), (border, rows)
