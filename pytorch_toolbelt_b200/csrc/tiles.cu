@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <utility>
 
 #include "common.cuh"
@@ -515,6 +516,60 @@ __global__ void __launch_bounds__(kThreads) slice_augment_fast_kernel(SliceArgs 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 3b. fast stand-alone TTA augment for 4-byte elements with H, W multiples of 32 (same scheme as 2b)
+// ------------------------------------------------------------------------------------------------
+template <int TTA>
+__global__ void __launch_bounds__(kThreads) tta_augment_fast_kernel(AugArgs a, int B, int C) {
+  using V = Views<TTA>;
+  __shared__ unsigned int sm[kChunkC * CH_STRIDE];
+  const int per_img = a.nbx * a.nby;
+  const int b = blockIdx.x / per_img;
+  const int blk = blockIdx.x - b * per_img;
+  const int by = blk / a.nbx, bx = blk - by * a.nbx;
+  const int R0 = by * BS, C0 = bx * BS;
+  const size_t plane = (size_t)a.H * a.W;
+  const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
+  const unsigned int* src = static_cast<const unsigned int*>(a.x) + (size_t)b * C * plane;
+  unsigned int* dst = static_cast<unsigned int*>(a.out) + (size_t)b * C * plane;
+  for (int c0 = 0; c0 < C; c0 += kChunkC) {
+    const int cc = min(kChunkC, C - c0);
+    if (c0) __syncthreads();
+    for (int ch = 0; ch < cc; ++ch) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)(c0 + ch) * plane + (size_t)(R0 + li) * a.W + C0 + 4 * lq));
+      unsigned int* s = sm + ch * CH_STRIDE + li * PITCH + 4 * lq;
+      s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int va = 0; va < V::count; ++va) {
+      const unsigned code = (V::packed >> (3 * va)) & 7u;
+      int base, step, oi0, oj0;
+      if (code & V_T) {
+        const int col = (code & V_FJ) ? (BS - 1 - li) : li;
+        const int row0 = (code & V_FI) ? (BS - 1 - 4 * lq) : 4 * lq;
+        base = row0 * PITCH + col;
+        step = (code & V_FI) ? -PITCH : PITCH;
+        oi0 = (code & V_FJ) ? a.W - C0 - BS : C0;
+        oj0 = (code & V_FI) ? a.H - R0 - BS : R0;
+      } else {
+        const int row = (code & V_FI) ? (BS - 1 - li) : li;
+        const int col0 = (code & V_FJ) ? (BS - 1 - 4 * lq) : 4 * lq;
+        base = row * PITCH + col0;
+        step = (code & V_FJ) ? -1 : 1;
+        oi0 = (code & V_FI) ? a.H - R0 - BS : R0;
+        oj0 = (code & V_FJ) ? a.W - C0 - BS : C0;
+      }
+      unsigned int* o = dst + (size_t)va * a.view_stride + (size_t)c0 * plane + (size_t)(oi0 + li) * a.W + oj0 + 4 * lq;
+      for (int ch = 0; ch < cc; ++ch) {
+        const unsigned int* s = sm + ch * CH_STRIDE + base;
+        *reinterpret_cast<uint4*>(o + (size_t)ch * plane) = make_uint4(s[0], s[step], s[2 * step], s[3 * step]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. stand-alone TTA de-augment (+ reduction)
 // ------------------------------------------------------------------------------------------------
@@ -781,6 +836,90 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------
+// Shared pieces of the TMA-pipelined kernels (7b, 7c)
+// ------------------------------------------------------------------------------------------------
+// Consumer thread -> pixel mapping: row li = 8*(warp&3) + (lane&7), 16-byte chunk cq = 4*(warp>>2) + (lane>>3)
+// (columns 4*cq .. 4*cq+3). A quarter-warp touches 8 rows with distinct (row & 7), so with the 128-byte swizzle the
+// LDS.128 of non-transposing views are bank-conflict free; transposing views read 4 scalars down a column.
+template <unsigned PACKED, int NV>
+struct TmaOffsets {
+  int vec[NV];     // float index of the float4 (non-transposing views)
+  int col[NV][4];  // float indices (transposing views)
+  __device__ __forceinline__ void init(int li, int cq) {
+    const int lj = 4 * cq;
+#pragma unroll
+    for (int va = 0; va < NV; ++va) {
+      const unsigned gc = view_inverse((PACKED >> (3 * va)) & 7u);
+      if (gc & V_T) {
+        const int cc = (gc & V_FJ) ? BS - 1 - li : li;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int rr = (gc & V_FI) ? BS - 1 - (lj + e) : lj + e;
+          col[va][e] = va * kBoxFloats + swz(rr, cc);
+        }
+        vec[va] = 0;
+      } else {
+        const int rr = (gc & V_FI) ? BS - 1 - li : li;
+        const int chunk = (gc & V_FJ) ? 7 - cq : cq;
+        vec[va] = va * kBoxFloats + rr * 32 + ((chunk ^ (rr & 7)) << 2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) col[va][e] = 0;
+      }
+    }
+  }
+  // sequential view-order sum of the (transformed) view values of this thread's 4 pixels
+  template <bool LINEAR>
+  __device__ __forceinline__ void reduce(const float* st, int red, float v[4]) const {
+#pragma unroll
+    for (int va = 0; va < NV; ++va) {
+      const unsigned gc = view_inverse((PACKED >> (3 * va)) & 7u);
+      float q[4];
+      if (gc & V_T) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = st[col[va][e]];
+      } else {
+        const float4 f = *reinterpret_cast<const float4*>(st + vec[va]);
+        if (gc & V_FJ) {
+          q[0] = f.w; q[1] = f.z; q[2] = f.y; q[3] = f.x;
+        } else {
+          q[0] = f.x; q[1] = f.y; q[2] = f.z; q[3] = f.w;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = LINEAR ? q[e] : red_pre<float>(red, q[e]);
+        v[e] = (va == 0) ? pv : add_rn(v[e], pv);
+      }
+    }
+  }
+};
+
+template <bool LINEAR, int NV>
+__device__ __forceinline__ float tma_post(int red, float v) {
+  if (LINEAR) return (red == TB_RED_MEAN) ? v / (float)NV : v;
+  return red_post<float>(red, v, NV);
+}
+
+// Producer side: issue the NV box loads of one (tile position `pos` in the map, channel k) for block origin (i0, j0).
+template <unsigned PACKED, int NV>
+__device__ __forceinline__ void tma_issue_views(float* stage, const CUtensorMap* map, uint64_t* bar, int pos, int K, int k,
+                                                int Th, int Tw, int i0, int j0) {
+#pragma unroll
+  for (int va = 0; va < NV; ++va) {
+    const unsigned gc = view_inverse((PACKED >> (3 * va)) & 7u);
+    int sr0, sc0;
+    if (gc & V_T) {
+      sr0 = (gc & V_FI) ? Th - j0 - BS : j0;
+      sc0 = (gc & V_FJ) ? Tw - i0 - BS : i0;
+    } else {
+      sr0 = (gc & V_FI) ? Th - i0 - BS : i0;
+      sc0 = (gc & V_FJ) ? Tw - j0 - BS : j0;
+    }
+    tma_load_box(stage + (size_t)va * kBoxFloats, map, bar, sc0, (pos * K + k) * Th + sr0, va);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 7b. TMA-pipelined output-stationary merge (requires Th, Tw, Sx, Sy multiples of 32 and a single pred tensor)
 //
 // Persistent CTAs: each CTA walks canvas blocks blockIdx.x, blockIdx.x + gridDim.x, ... and the stage ring
@@ -860,20 +999,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
               fence_proxy_async();
               mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
               const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
-#pragma unroll
-              for (int va = 0; va < NV; ++va) {
-                const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
-                int sr0, sc0;
-                if (gc & V_T) {
-                  sr0 = (gc & V_FI) ? g.Th - j0 - BS : j0;
-                  sc0 = (gc & V_FJ) ? g.Tw - i0 - BS : i0;
-                } else {
-                  sr0 = (gc & V_FI) ? g.Th - i0 - BS : i0;
-                  sc0 = (gc & V_FJ) ? g.Tw - j0 - BS : j0;
-                }
-                const int row = (pos * a.K + k) * g.Th + sr0;
-                tma_load_box(boxes + ((size_t)s * NV + va) * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi], &full[s], sc0, row, va);
-              }
+              tma_issue_views<V::packed, NV>(boxes + (size_t)s * NV * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi], &full[s], pos,
+                                             a.K, k, g.Th, g.Tw, i0, j0);
               ++it;
             }
           }
@@ -893,29 +1020,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
   const int lj = 4 * cq;
   const int rows = a.y1 - a.y0;
 
-  // loop-invariant shared-memory offsets: non-transposing views read one float4 (reversed when flipped along
-  // columns); transposing views read 4 scalars down a column
-  int off_vec[NV];      // float index of the float4 (non-transposing views)
-  int off_col[NV][4];   // float indices (transposing views)
-#pragma unroll
-  for (int va = 0; va < NV; ++va) {
-    const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
-    if (gc & V_T) {
-      const int cc = (gc & V_FJ) ? BS - 1 - li : li;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int rr = (gc & V_FI) ? BS - 1 - (lj + e) : lj + e;
-        off_col[va][e] = va * kBoxFloats + swz(rr, cc);
-      }
-      off_vec[va] = 0;
-    } else {
-      const int rr = (gc & V_FI) ? BS - 1 - li : li;
-      const int chunk = (gc & V_FJ) ? 7 - cq : cq;
-      off_vec[va] = va * kBoxFloats + rr * 32 + ((chunk ^ (rr & 7)) << 2);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) off_col[va][e] = 0;
-    }
-  }
+  TmaOffsets<V::packed, NV> offs;  // loop-invariant shared-memory offsets of this thread's 4 pixels
+  offs.init(li, cq);
 
   int it = 0;
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -952,38 +1058,12 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
           mbar_wait(&full[s], ph);
           const float* st = boxes + (size_t)s * NV * kBoxFloats;
           float v[4];
-#pragma unroll
-          for (int va = 0; va < NV; ++va) {
-            const unsigned gc = view_inverse((V::packed >> (3 * va)) & 7u);
-            float q[4];
-            if (gc & V_T) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) q[e] = st[off_col[va][e]];
-            } else {
-              const float4 f = *reinterpret_cast<const float4*>(st + off_vec[va]);
-              if (gc & V_FJ) {
-                q[0] = f.w; q[1] = f.z; q[2] = f.y; q[3] = f.x;
-              } else {
-                q[0] = f.x; q[1] = f.y; q[2] = f.z; q[3] = f.w;
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float pv = LINEAR ? q[e] : red_pre<float>(a.red, q[e]);
-              v[e] = (va == 0) ? pv : add_rn(v[e], pv);
-            }
-          }
-          // Release the stage only after this warp's reads have RETURNED: the release is made data-dependent on
-          // the loaded values (a load still in flight when the producer's TMA refill lands would be a WAR race).
+          offs.template reduce<LINEAR>(st, a.red, v);
           if (a.debug & 1) asm volatile("bar.sync 1, 256;" ::: "memory");  // all consumer warps done reading
           mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float r4;
-            if (LINEAR)
-              r4 = (a.red == TB_RED_MEAN) ? v[e] / (float)NV : v[e];
-            else
-              r4 = red_post<float>(a.red, v[e], NV);
+            const float r4 = tma_post<LINEAR, NV>(a.red, v[e]);
             acc[e] = add_rn(acc[e], mul_rn(r4, wt[e]));
             den[e] = add_rn(den[e], wt[e]);
           }
@@ -1009,6 +1089,124 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
               if (oj + e >= 0 && oj + e < a.W) o[oj + e] = acc[e] / den[e];
           }
         }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 7c. TMA-pipelined per-tile de-augment (stand-alone tta.*_image_deaugment) and streaming scatter merge
+//     (TileMerger.integrate_batch with the de-augment fused). Same ring as 7b; a block is a 32x32 patch of one tile.
+// ------------------------------------------------------------------------------------------------
+struct TileTmaArgs {
+  float* out;    // DEAUG: [n,K,Th,Tw]
+  float* image;  // SCATTER: [K,Hp,Wp]
+  float* norm;   // SCATTER: [Hp,Wp] or null
+  TileXY xy;     // SCATTER: canvas coordinates of the tiles
+  int n, K, Th, Tw, Hp, Wp, nbx, nby, red;
+  WeightDev<float> w;
+};
+
+template <int TTA, bool LINEAR, bool SCATTER>
+__global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaArgs a, const __grid_constant__ TmaMaps<1> maps,
+                                                                       int nblocks) {
+  using V = Views<TTA>;
+  constexpr int NV = V::count;
+  constexpr int STAGES = tma_stages(NV);
+  extern __shared__ __align__(1024) float smem_boxes[];
+  float* boxes = smem_boxes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * NV * kBoxFloats);
+  uint64_t* empty = full + STAGES;
+  if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kTmaConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int per_tile = a.nbx * a.nby;
+
+  if (warp == kTmaConsumerWarps) {
+    if (lane == 0) {
+      int it = 0;
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int t = blk / per_tile, rem = blk - t * per_tile;
+        const int i0 = (rem / a.nbx) * BS, j0 = (rem % a.nbx) * BS;
+        for (int k = 0; k < a.K; ++k) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          fence_proxy_async();  // generic-proxy reads of the slot before the async-proxy refill (see 7b)
+          mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
+          tma_issue_views<V::packed, NV>(boxes + (size_t)s * NV * kBoxFloats, &maps.m[0], &full[s], t, a.K, k, a.Th, a.Tw, i0, j0);
+          ++it;
+        }
+      }
+    }
+    return;
+  }
+
+  const int li = 8 * (warp & 3) + (lane & 7);
+  const int cq = 4 * (warp >> 2) + (lane >> 3);
+  const int lj = 4 * cq;
+  TmaOffsets<V::packed, NV> offs;
+  offs.init(li, cq);
+  const size_t plane = (size_t)a.Th * a.Tw;
+  int it = 0;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int t = blk / per_tile, rem = blk - t * per_tile;
+    const int i = (rem / a.nbx) * BS + li, j = (rem % a.nbx) * BS + lj;
+    float wt[4] = {1.f, 1.f, 1.f, 1.f};
+    size_t cpix = 0;
+    bool vec_ok = true;
+    if (SCATTER) {
+      int x0, y0;
+      a.xy.get(t, x0, y0);
+      if (a.w.kind == TB_W_TABLE) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)i * a.Tw + j));
+        wt[0] = w4.x; wt[1] = w4.y; wt[2] = w4.z; wt[3] = w4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wt[e] = weight_at<float>(a.w, i, j + e);
+      }
+      cpix = (size_t)(y0 + i) * a.Wp + (x0 + j);
+      vec_ok = ((x0 & 3) == 0) && ((a.Wp & 3) == 0);
+    }
+    for (int k = 0; k < a.K; ++k) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      float v[4];
+      offs.template reduce<LINEAR>(boxes + (size_t)s * NV * kBoxFloats, a.red, v);
+      mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = tma_post<LINEAR, NV>(a.red, v[e]);
+      if (SCATTER) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = mul_rn(v[e], wt[e]);
+        float* dst = a.image + (size_t)k * a.Hp * a.Wp + cpix;
+        if (vec_ok) {
+          red_add4(dst, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) red_add1(dst + e, v[e]);
+        }
+      } else {
+        __stcs(reinterpret_cast<float4*>(a.out + ((size_t)t * a.K + k) * plane + (size_t)i * a.Tw + j),
+               make_float4(v[0], v[1], v[2], v[3]));
+      }
+      ++it;
+    }
+    if (SCATTER && a.norm) {
+      float* dst = a.norm + cpix;
+      if (vec_ok) {
+        red_add4(dst, wt);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red_add1(dst + e, wt[e]);
       }
     }
   }
@@ -1131,6 +1329,30 @@ static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const TmaMaps<MAX
   return launch_merge_all_tma_impl<TTA, false, MAXB>(a, maps, nblocks, s);
 }
 
+template <int TTA, bool LINEAR, bool SCATTER>
+static cudaError_t launch_tile_deaug_tma_impl(const TileTmaArgs& a, const TmaMaps<1>& maps, int nblocks, cudaStream_t s) {
+  constexpr int NV = Views<TTA>::count;
+  const size_t smem = tma_smem_bytes(NV);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(tile_deaug_tma_kernel<TTA, LINEAR, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_deaug_tma_kernel<TTA, LINEAR, SCATTER>, kTmaThreads, smem);
+    if (e != cudaSuccess) return e;
+    ctas_per_sm = n > 0 ? n : 1;
+  }
+  const int grid = std::min(nblocks, sm_count() * ctas_per_sm);
+  tile_deaug_tma_kernel<TTA, LINEAR, SCATTER><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
+  return cudaGetLastError();
+}
+
+template <int TTA, bool SCATTER>
+static cudaError_t launch_tile_deaug_tma(const TileTmaArgs& a, const TmaMaps<1>& maps, int nblocks, cudaStream_t s) {
+  if (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) return launch_tile_deaug_tma_impl<TTA, true, SCATTER>(a, maps, nblocks, s);
+  return launch_tile_deaug_tma_impl<TTA, false, SCATTER>(a, maps, nblocks, s);
+}
+
 // Geometry test for the TMA path (everything on the 32-pixel lattice, 16-byte aligned side buffers).
 static bool tma_geometry_ok(const tb_grid* grid, int Wp, const float* init_num, const float* init_den, int raw,
                             const float* out_num, const float* out_den, const tb_weight* weight) {
@@ -1243,7 +1465,10 @@ int tb_tta_augment(const void* x, int elem_bytes, int B, int C, int H, int W, in
     case 1: tta_augment_kernel<unsigned char, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
     case 2: tta_augment_kernel<unsigned short, false><<<(unsigned)blocks, kThreads, 0, s>>>(a); break;
     case 4:
-      if (vec)
+      if ((H % BS == 0) && (W % BS == 0) && aligned16(x) && aligned16(out)) {
+        const long long fblocks = (long long)B * a.nbx * a.nby;
+        TB_DISPATCH_TTA(tta, tta_augment_fast_kernel<TTA_><<<(unsigned)fblocks, kThreads, 0, s>>>(a, B, C));
+      } else if (vec)
         tta_augment_kernel<unsigned int, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);
       else
         tta_augment_kernel<unsigned int, false><<<(unsigned)blocks, kThreads, 0, s>>>(a);
@@ -1314,6 +1539,21 @@ int tb_tta_deaugment(const void* x, int dtype, int B, int C, int H, int W, int t
   TB_REQUIRE(blocks < (1ll << 31), TB_ERR_ARG, "tb_tta_deaugment: grid too large");
   const bool al = (H % 4 == 0) && (W % 4 == 0) && aligned16(x) && aligned16(out);
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == TB_F32 && reduction != TB_RED_NONE && al && (H % BS == 0) && (W % BS == 0) && !tb_force_generic_merge()) {
+    // TMA ring: the [A*B, C, H, W] stack as the rank-3 tensor {W, B*C*H, A}
+    TmaMaps<1> maps;
+    if (make_pred_tensor_map((const float*)x, B, C, H, W, a.views.count, &maps.m[0])) {
+      TileTmaArgs ta{};
+      ta.out = (float*)out; ta.n = B; ta.K = C; ta.Th = H; ta.Tw = W; ta.nbx = W / BS; ta.nby = H / BS; ta.red = reduction;
+      const long long nb = (long long)B * ta.nbx * ta.nby;
+      if (nb < (1ll << 31)) {
+        cudaError_t e = cudaErrorInvalidValue;
+        TB_DISPATCH_TTA(tta, e = (launch_tile_deaug_tma<TTA_, false>(ta, maps, (int)nb, s)));
+        if (e != cudaSuccess) return cuda_fail(e, "tile_deaug_tma_kernel");
+        return TB_OK;
+      }
+    }
+  }
   if (dtype == TB_F32) {
     if (al) {
       TB_DISPATCH_TTA(tta, tta_deaugment_kernel<float, true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
@@ -1362,6 +1602,19 @@ static int launch_deaugment_merge(const void* pred, const int32_t* xy, int xy_is
   if (blocks >= (1ll << 31)) return fail(TB_ERR_ARG, "tb_deaugment_merge: grid too large");
   const bool al = (Th % 4 == 0) && (Tw % 4 == 0) && aligned16(pred) && aligned16(image) &&
                   (!norm || aligned16(norm)) && (weight->kind != TB_W_TABLE || aligned16(weight->table));
+  if (std::is_same<T, float>::value && al && (Th % BS == 0) && (Tw % BS == 0) && !tb_force_generic_merge()) {
+    TmaMaps<1> maps;
+    if (make_pred_tensor_map((const float*)pred, n, K, Th, Tw, views.count, &maps.m[0])) {
+      TileTmaArgs ta{};
+      ta.image = (float*)image; ta.norm = (float*)norm; ta.xy = a.xy; ta.n = n; ta.K = K; ta.Th = Th; ta.Tw = Tw;
+      ta.Hp = Hp; ta.Wp = Wp; ta.nbx = Tw / BS; ta.nby = Th / BS; ta.red = reduction;
+      make_weight<float>(weight, Th, Tw, &ta.w);
+      cudaError_t e = cudaErrorInvalidValue;
+      TB_DISPATCH_TTA(tta, e = (launch_tile_deaug_tma<TTA_, true>(ta, maps, (int)blocks, s)));
+      if (e != cudaSuccess) return cuda_fail(e, "tile_deaug_tma_kernel(scatter)");
+      return TB_OK;
+    }
+  }
   if (al) {
     TB_DISPATCH_TTA(tta, deaugment_merge_kernel<T, true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
   } else {

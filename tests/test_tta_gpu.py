@@ -167,3 +167,43 @@ def test_generalized_tta_wrapper():
     ms = tta.MultiscaleTTA(model, [0, 16, -16])
     with torch.no_grad():
         assert ms(x).shape == (2, 2, 32, 32)
+
+
+def test_tma_and_plain_deaugment_kernels_agree_bitwise():
+    """tb_tta_deaugment / tb_deaugment_merge have a TMA-ring and a plain-load implementation; same arithmetic."""
+    import os
+
+    from pytorch_toolbelt_b200.inference.tiles import CudaTileMerger, ImageSlicer
+    from pytorch_toolbelt_b200._native import TB
+
+    g = torch.Generator().manual_seed(21)
+    for group, (aug, deaug) in AUG.items():
+        A = len(AO.GROUPS[group])
+        y = (torch.rand((A * 3, 5, 96, 96), generator=g) * 0.9 + 0.05).cuda()
+        for red in ("mean", "sum", "gmean", "logodd"):
+            fast = deaug(y, reduction=red)
+            os.environ["TB200_FORCE_GENERIC_MERGE"] = "1"
+            try:
+                slow = deaug(y, reduction=red)
+            finally:
+                del os.environ["TB200_FORCE_GENERIC_MERGE"]
+            assert torch.equal(fast, slow), (group, red)
+    s = ImageSlicer((700, 500, 3), 128, 64, weight="pyramid")
+    pred = torch.randn(8 * len(s.crops), 3, 128, 128, generator=g).cuda()
+    results = []
+    for force in (False, True):
+        if force:
+            os.environ["TB200_FORCE_GENERIC_MERGE"] = "1"
+        try:
+            m = CudaTileMerger(s.target_shape, 3, s.weight)
+            for b0 in range(0, len(s.crops), 9):
+                idx = torch.arange(b0, min(b0 + 9, len(s.crops)))
+                chunk = pred.view(8, len(s.crops), 3, 128, 128)[:, idx].reshape(-1, 3, 128, 128).contiguous()
+                m.integrate_batch(chunk, s.crops[idx.numpy()], tta=TB.TTA_D4)
+            results.append((m.image.clone(), m.norm_mask.clone()))
+        finally:
+            os.environ.pop("TB200_FORCE_GENERIC_MERGE", None)
+    # float atomics: order differs between runs, compare to buffer scale
+    scale = results[1][0].abs().max()
+    assert (results[0][0] - results[1][0]).abs().max() <= 1e-5 * scale
+    assert (results[0][1] - results[1][1]).abs().max() <= 1e-5 * results[1][1].abs().max()
