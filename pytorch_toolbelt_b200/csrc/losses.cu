@@ -111,10 +111,11 @@ struct FocalDev {
 };
 
 // One element: loss L, focal term F (as used by the normalisation), dL/dx and dF/dx (0 where masked).
-__device__ __forceinline__ void focal_elem(const FocalDev& f, float x, float t, float prob, float dprob_dx, int c,
-                                           float& L, float& F, float& dL, float& dF) {
+// sig = sigmoid(x) and softplus = log1p(exp(-|x|)) are passed in so that one exp serves both
+__device__ __forceinline__ void focal_elem(const FocalDev& f, float x, float t, float prob, float dprob_dx, float sig,
+                                           float softplus, int c, float& L, float& F, float& dL, float& dF) {
   const tb_focal_params& p = f.p;
-  const float ce = bce_logits(x, t);
+  const float ce = fmaxf(x, 0.f) - x * t + softplus;
   const float pt = prob * t + (1.f - prob) * (1.f - t);
   const float dpt = dprob_dx * (2.f * t - 1.f);
   float focal, dfocal;
@@ -136,7 +137,6 @@ __device__ __forceinline__ void focal_elem(const FocalDev& f, float x, float t, 
   float scale = 1.f;
   if (p.has_alpha) scale = p.alpha * t + (1.f - p.alpha) * (1.f - t);
   if (f.cw) scale *= __ldg(f.cw + c);
-  const float sig = sigmoidf_(x);
   L = focal * ce * scale;
   dL = (dfocal * ce + focal * (sig - t)) * scale;
   F = focal;
@@ -200,9 +200,11 @@ __global__ void __launch_bounds__(kLT) focal_kernel(FocalArgs a) {
     float le[VW], ge[VW];
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
-      const float pr = sigmoidf_(xs[e]);
+      const float ex = __expf(-fabsf(xs[e]));
+      const float inv = 1.f / (1.f + ex);
+      const float pr = xs[e] >= 0.f ? inv : ex * inv;  // sigmoid(x) from the same exp as the softplus term
       float L, F, dL, dF;
-      focal_elem(a.f, xs[e], tv[e], pr, pr * (1.f - pr), c, L, F, dL, dF);
+      focal_elem(a.f, xs[e], tv[e], pr, pr * (1.f - pr), pr, log1pf(ex), c, L, F, dL, dF);
       if (PASS != 2) {
         acc[0] += (double)L;
         acc[1] += (double)F;
@@ -276,7 +278,7 @@ struct PixelFocalArgs {
   float gscale;
 };
 
-template <int PASS>
+template <int PASS, int CB>
 __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
   const long long npix = a.B * a.inner;
   const tb_focal_params& p = a.f.p;
@@ -290,14 +292,16 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
   for (long long pix = (long long)blockIdx.x * kLT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kLT) {
     const long long b = pix / a.inner, pos = pix - b * a.inner;
     const float* xp = a.x + b * a.C * a.inner + pos;
-    float xv[kMaxC];
+    float xv[CB];
     float mx = -INFINITY;
-    for (int c = 0; c < a.C; ++c) {
+    #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) {
       xv[c] = __ldcs(xp + (long long)c * a.inner);
       mx = fmaxf(mx, xv[c]);
     }
     float den = 0.f;
-    for (int c = 0; c < a.C; ++c) den += __expf(xv[c] - mx);
+    #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) den += __expf(xv[c] - mx);
     const float inv_den = 1.f / den;
 
     if (a.mode == 0) {
@@ -306,8 +310,9 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
       const bool valid = lab != a.ignore_label;
       const int label = valid ? (int)lab : 0;  // masked_fill(ignore, 0) then one_hot
       float Lpix = 0.f, Fpix = 0.f, S_G = 0.f, S_F = 0.f;
-      float G[kMaxC], Fd[kMaxC], direct[kMaxC];
-      for (int c = 0; c < a.C; ++c) {
+      float G[CB], Fd[CB], direct[CB];
+      #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) {
         const float prob = __expf(xv[c] - mx) * inv_den;
         const float oh = (c == label) ? 1.f : 0.f;
         const float pt = (1.f - oh) * prob + oh * (1.f - prob);
@@ -343,7 +348,8 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
         if (a.loss_elem) a.loss_elem[pix] = (PASS == 2) ? Lpix * invN : Lpix;
         if (a.grad) {
           float* gp = a.grad + b * a.C * a.inner + pos;
-          for (int c = 0; c < a.C; ++c) {
+          #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) {
             const float prob = __expf(xv[c] - mx) * inv_den;
             const float dL = prob * (G[c] - S_G) + direct[c];
             float g = dL;
@@ -354,9 +360,10 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
       }
     } else {
       // ---- focal_loss_with_logits(activation="softmax"): p = softmax, CE stays element-wise BCE (:61-67) ----
-      float L[kMaxC], F[kMaxC], A[kMaxC], Bq[kMaxC], dLx[kMaxC];
+      float L[CB], F[CB], A[CB], Bq[CB], dLx[CB];
       float S_A = 0.f, S_B = 0.f;
-      for (int c = 0; c < a.C; ++c) {
+      #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) {
         const float prob = __expf(xv[c] - mx) * inv_den;
         float t;
         if (a.t_kind == TB_T_LABELS_I64) {
@@ -368,13 +375,14 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
         }
         // split dL into the part through prob (dprob = 1 here) and the direct BCE part
         float Lc, Fc, dLp, dFp;
-        focal_elem(a.f, xv[c], t, prob, 1.f, c, Lc, Fc, dLp, dFp);
+        const float sg = sigmoidf_(xv[c]);
+        focal_elem(a.f, xv[c], t, prob, 1.f, sg, log1pf(__expf(-fabsf(xv[c]))), c, Lc, Fc, dLp, dFp);
         // focal_elem folds focal*(sigmoid-t)*scale into dL: recover the prob-path derivative separately
         float scale = 1.f;
         if (p.has_alpha) scale = p.alpha * t + (1.f - p.alpha) * (1.f - t);
         if (a.f.cw) scale *= __ldg(a.f.cw + c);
         const bool ign = p.has_ignore && t == p.ignore_index;
-        const float direct = ign ? 0.f : Fc * (sigmoidf_(xv[c]) - t) * scale;
+        const float direct = ign ? 0.f : Fc * (sg - t) * scale;
         const float via_p = dLp - direct;  // = dfocal/dprob * ce * scale
         L[c] = Lc; F[c] = Fc; A[c] = via_p; Bq[c] = dFp; dLx[c] = direct;
         S_A += via_p * prob;
@@ -385,7 +393,8 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
         }
       }
       if (PASS != 1) {
-        for (int c = 0; c < a.C; ++c) {
+        #pragma unroll
+    for (int c = 0; c < CB; ++c) if (c < a.C) {
           const long long o = b * a.C * a.inner + (long long)c * a.inner + pos;
           const float prob = __expf(xv[c] - mx) * inv_den;
           const float dL = prob * (A[c] - S_A) + dLx[c];
@@ -484,14 +493,82 @@ __global__ void __launch_bounds__(kLT) region_stats_elem_finalize(const double* 
   }
 }
 
-// multiclass: one thread per pixel, softmax over C, per-class sums accumulated in shared memory per CTA
+// multiclass: one thread per pixel, softmax over C. CB <= 8: per-thread register accumulators, one block reduction
+// at the end; larger C: warp-aggregated shared-memory accumulation per pixel.
+template <int CB>
+__global__ void __launch_bounds__(kLT) region_stats_mc_small_kernel(RegionArgs a) {
+  const long long npix = a.B * a.inner;
+  const long long* labels = static_cast<const long long*>(a.t);
+  float accI[CB], accS[CB], accT[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) accI[c] = accS[c] = accT[c] = 0.f;
+  double dI[CB], dS[CB], dT[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) dI[c] = dS[c] = dT[c] = 0.0;
+  int since_flush = 0;
+  for (long long pix = (long long)blockIdx.x * kLT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kLT) {
+    const long long b = pix / a.inner, pos = pix - b * a.inner;
+    const float* xp = a.x + b * a.C * a.inner + pos;
+    const long long lab = __ldg(labels + pix);
+    const bool valid = !(a.p.has_ignore && (float)lab == a.p.ignore_index);
+    float xv[CB];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < a.C) {
+        xv[c] = __ldcs(xp + (long long)c * a.inner);
+        mx = fmaxf(mx, xv[c]);
+      }
+    float inv_den = 1.f;
+    if (a.p.from_logits) {
+      float den = 0.f;
+#pragma unroll
+      for (int c = 0; c < CB; ++c)
+        if (c < a.C) {
+          xv[c] = __expf(xv[c] - mx);
+          den += xv[c];
+        }
+      inv_den = 1.f / den;
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+      if (c < a.C) {
+        const float pr = valid ? xv[c] * inv_den : 0.f;
+        const float t = (valid && lab == c) ? 1.f : 0.f;
+        accI[c] += pr * t;
+        accS[c] += pr + t;
+        accT[c] += t;
+      }
+    if (++since_flush == 64) {  // keep the float partials short: flush into doubles
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        dI[c] += accI[c]; dS[c] += accS[c]; dT[c] += accT[c];
+        accI[c] = accS[c] = accT[c] = 0.f;
+      }
+      since_flush = 0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    dI[c] += accI[c]; dS[c] += accS[c]; dT[c] += accT[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CB; ++c) {
+    double v[3] = {dI[c], dS[c], dT[c]};
+    block_reduce<3>(v);
+    if (threadIdx.x == 0 && c < a.C) {
+      double* o = a.partials + ((size_t)blockIdx.x * a.C + c) * 3;
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kLT) region_stats_mc_kernel(RegionArgs a) {
   extern __shared__ double sh_stats[];  // [C][3]
   for (int i = threadIdx.x; i < 3 * a.C; i += kLT) sh_stats[i] = 0.0;
   __syncthreads();
   const long long npix = a.B * a.inner;
   const long long* labels = static_cast<const long long*>(a.t);
-  // per-thread register accumulators for the first 8 classes (the common case), shared atomics beyond
   // uniform trip count: the warp shuffles below need every lane of the warp in the loop
   for (long long base = (long long)blockIdx.x * kLT; base < npix; base += (long long)gridDim.x * kLT) {
     const long long pix_raw = base + threadIdx.x;
@@ -642,6 +719,38 @@ __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
       }
       if (!a.p.from_logits) {
         for (int c = 0; c < a.C; ++c) gp[(long long)c * a.inner] = sh_coef[2 * c] * (lab == c ? 1.f : 0.f) + sh_coef[2 * c + 1];
+        continue;
+      }
+      if (a.C <= 8) {
+        float pv[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.C) {
+            pv[c] = __ldcs(xp + (long long)c * a.inner);
+            mx = fmaxf(mx, pv[c]);
+          }
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.C) {
+            pv[c] = __expf(pv[c] - mx);
+            den += pv[c];
+          }
+        const float inv_den = 1.f / den;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.C) {
+            pv[c] *= inv_den;
+            dot += (sh_coef[2 * c] * (lab == c ? 1.f : 0.f) + sh_coef[2 * c + 1]) * pv[c];
+          }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.C) {
+            const float gc = sh_coef[2 * c] * (lab == c ? 1.f : 0.f) + sh_coef[2 * c + 1];
+            __stcs(gp + (long long)c * a.inner, pv[c] * (gc - dot));
+          }
         continue;
       }
       float mx = -INFINITY;
@@ -858,6 +967,19 @@ size_t tb_loss_workspace_bytes(int64_t B, int C, int64_t inner) {
   return align_up(bytes, 256) + 256;
 }
 
+}  // extern "C"
+
+template <int PASS>
+static void launch_pixel_focal(const PixelFocalArgs& a, int grid, cudaStream_t s) {
+  if (a.C <= 4) pixel_focal_kernel<PASS, 4><<<grid, kLT, 0, s>>>(a);
+  else if (a.C <= 8) pixel_focal_kernel<PASS, 8><<<grid, kLT, 0, s>>>(a);
+  else if (a.C <= 16) pixel_focal_kernel<PASS, 16><<<grid, kLT, 0, s>>>(a);
+  else if (a.C <= 32) pixel_focal_kernel<PASS, 32><<<grid, kLT, 0, s>>>(a);
+  else pixel_focal_kernel<PASS, kMaxC><<<grid, kLT, 0, s>>>(a);
+}
+
+extern "C" {
+
 static int reduction_ok(int reduction) { return reduction >= TB_LOSS_NONE && reduction <= TB_LOSS_BATCHWISE; }
 
 int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C, int64_t inner,
@@ -887,14 +1009,14 @@ int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C
     a.partials = partials; a.sums = nullptr;
     double* sums = partials + 2 * (size_t)grid;
     if (!p->normalized) {
-      pixel_focal_kernel<0><<<grid, kLT, 0, s>>>(a);
+      launch_pixel_focal<0>(a, grid, s);
       focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, elem_out ? nullptr : loss_out, p->reduction, 0, p->eps, numel);
     } else {
-      pixel_focal_kernel<1><<<grid, kLT, 0, s>>>(a);
+      launch_pixel_focal<1>(a, grid, s);
       focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, elem_out ? nullptr : loss_out, p->reduction, 1, p->eps, numel);
       if (elem_out || grad) {
         a.sums = sums;
-        pixel_focal_kernel<2><<<grid, kLT, 0, s>>>(a);
+        launch_pixel_focal<2>(a, grid, s);
       }
     }
     TB_LAUNCH_CHECK("pixel_focal_kernel");
@@ -980,14 +1102,14 @@ int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C,
   a.partials = partials; a.sums = nullptr;
   float* scalar_out = (elem_out || batchwise) ? nullptr : loss_out;
   if (!normalized) {
-    pixel_focal_kernel<0><<<grid, kLT, 0, s>>>(a);
+    launch_pixel_focal<0>(a, grid, s);
     focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, scalar_out, reduction, 0, eps, npos);
   } else {
-    pixel_focal_kernel<1><<<grid, kLT, 0, s>>>(a);
+    launch_pixel_focal<1>(a, grid, s);
     focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, scalar_out, reduction, 1, eps, npos);
     if (elem_buf || grad) {
       a.sums = sums;
-      pixel_focal_kernel<2><<<grid, kLT, 0, s>>>(a);
+      launch_pixel_focal<2>(a, grid, s);
     }
   }
   if (batchwise) sum_dim0_kernel<<<loss_grid(inner), kLT, 0, s>>>(elem_buf, B, inner, loss_out);
@@ -1009,7 +1131,12 @@ int tb_dice_stats(const float* x, const void* t, int t_kind, int64_t B, int C, i
     TB_REQUIRE(t_kind == TB_T_LABELS_I64, TB_ERR_ARG, "tb_dice_stats: multiclass needs int64 labels");
     TB_REQUIRE(C <= 1024, TB_ERR_UNSUPPORTED, "tb_dice_stats: multiclass supports C <= 1024");
     const int grid = loss_grid(B * inner);
-    region_stats_mc_kernel<<<grid, kLT, 3 * C * sizeof(double), s>>>(a);
+    if (C <= 4)
+      region_stats_mc_small_kernel<4><<<grid, kLT, 0, s>>>(a);
+    else if (C <= 8)
+      region_stats_mc_small_kernel<8><<<grid, kLT, 0, s>>>(a);
+    else
+      region_stats_mc_kernel<<<grid, kLT, 3 * C * sizeof(double), s>>>(a);
     region_stats_mc_finalize<<<C, kLT, 0, s>>>(a.partials, grid, C, stats_out);
   } else {
     TB_REQUIRE(t_kind == TB_T_DENSE_F32, TB_ERR_ARG, "tb_dice_stats: binary/multilabel need a dense f32 target");
