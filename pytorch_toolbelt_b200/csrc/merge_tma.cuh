@@ -24,9 +24,12 @@ constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kBoxFloats = 32 * 32;
 constexpr int kBoxBytes = kBoxFloats * 4;
 
-__host__ __device__ constexpr int tma_stages(int views) { return views >= 8 ? 3 : (views >= 3 ? 6 : 10); }
-__host__ __device__ constexpr size_t tma_smem_bytes(int views) {
-  return (size_t)tma_stages(views) * views * kBoxBytes + 1024 /*alignment slack*/ + 2 * 16 * sizeof(uint64_t);
+// DEEP = one CTA per SM with a ring that fills the whole 227 KB of shared memory (7 x 32 KB for 8 views)
+__host__ __device__ constexpr int tma_stages(int views, bool deep = false) {
+  return deep ? (views >= 8 ? 7 : (views >= 3 ? 14 : 16)) : (views >= 8 ? 3 : (views >= 3 ? 6 : 10));
+}
+__host__ __device__ constexpr size_t tma_smem_bytes(int views, bool deep = false) {
+  return (size_t)tma_stages(views, deep) * views * kBoxBytes + 2 * 16 * sizeof(uint64_t);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,6 +72,20 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(row), "r"(view)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_box_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int col, int row, int view,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(col), "r"(row), "r"(view), "l"(policy)
       : "memory");
 }
 

@@ -463,8 +463,9 @@ __device__ __forceinline__ void load_block_fast(const SliceArgs& a, const SrcT* 
   }
 }
 
-template <typename SrcT, int TTA>
-__global__ void __launch_bounds__(kThreads) slice_augment_fast_kernel(SliceArgs a) {
+// VAR bit0: ask for 6 resident CTAs per SM (register cap 40); bit1: streaming (evict-first) stores
+template <typename SrcT, int TTA, int VAR>
+__global__ void __launch_bounds__(kThreads, (VAR & 1) ? 6 : 1) slice_augment_fast_kernel(SliceArgs a) {
   using V = Views<TTA>;
   __shared__ float sm[kChunkC * CH_STRIDE];
   const int per_tile = a.nbx * a.nby;
@@ -510,12 +511,56 @@ __global__ void __launch_bounds__(kThreads) slice_augment_fast_kernel(SliceArgs 
       for (int ch = 0; ch < cc; ++ch) {
         const float* s = sm + ch * CH_STRIDE + base;
         const float4 q = make_float4(s[0], s[step], s[2 * step], s[3 * step]);
-        *reinterpret_cast<float4*>(o + (size_t)ch * plane) = q;
+        if (VAR & 2)
+          __stcs(reinterpret_cast<float4*>(o + (size_t)ch * plane), q);
+        else
+          *reinterpret_cast<float4*>(o + (size_t)ch * plane) = q;
       }
     }
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// 2c. slice without TTA (one view): nothing is reused, so no shared memory: every thread converts 4 consecutive
+//     pixels of one tile row (all channels) and writes one float4 per channel plane.
+// ------------------------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void __launch_bounds__(kThreads) slice_plain_kernel(SliceArgs a) {
+  const int groups_per_row = a.Tw >> 2;  // host guarantees Tw % 4 == 0
+  const long long per_tile = (long long)a.Th * groups_per_row;
+  const long long total = per_tile * a.n;
+  const SrcT* img = static_cast<const SrcT*>(a.img);
+  const size_t plane = (size_t)a.Th * a.Tw;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+    const int t = (int)(idx / per_tile);
+    const int rem = (int)(idx - (long long)t * per_tile);
+    const int i = rem / groups_per_row, j = (rem - i * groups_per_row) << 2;
+    const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+    const int gy = y0 + i, gx = x0 + j;
+    const bool interior = gy >= 0 && gy < a.H && gx >= 0 && gx + 3 < a.W;
+    const int sy = interior ? gy : border_remap(gy, 0, a.H, a.border);
+    int sx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sx[e] = interior ? gx + e : border_remap(gx + e, 0, a.W, a.border);
+    float* o = a.out + (size_t)t * a.C * plane + (size_t)i * a.Tw + j;
+    for (int c = 0; c < a.C; ++c) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (sy < 0 || sx[e] < 0)
+          v[e] = c < 4 ? a.bval[c] : 0.f;
+        else if (a.layout == TB_HWC)
+          v[e] = to_f32(img[((size_t)sy * a.W + sx[e]) * a.C + c]);
+        else
+          v[e] = to_f32(img[((size_t)c * a.H + sy) * a.W + sx[e]]);
+        if (a.has_affine && c < 8) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[c]), a.bias[c]);
+      }
+      __stcs(reinterpret_cast<float4*>(o + (size_t)c * plane), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // 3b. fast stand-alone TTA augment for 4-byte elements with H, W multiples of 32 (same scheme as 2b)
@@ -903,7 +948,7 @@ __device__ __forceinline__ float tma_post(int red, float v) {
 // Producer side: issue the NV box loads of one (tile position `pos` in the map, channel k) for block origin (i0, j0).
 template <unsigned PACKED, int NV>
 __device__ __forceinline__ void tma_issue_views(float* stage, const CUtensorMap* map, uint64_t* bar, int pos, int K, int k,
-                                                int Th, int Tw, int i0, int j0) {
+                                                int Th, int Tw, int i0, int j0, bool hint = false, uint64_t policy = 0) {
 #pragma unroll
   for (int va = 0; va < NV; ++va) {
     const unsigned gc = view_inverse((PACKED >> (3 * va)) & 7u);
@@ -915,7 +960,10 @@ __device__ __forceinline__ void tma_issue_views(float* stage, const CUtensorMap*
       sr0 = (gc & V_FI) ? Th - i0 - BS : i0;
       sc0 = (gc & V_FJ) ? Tw - j0 - BS : j0;
     }
-    tma_load_box(stage + (size_t)va * kBoxFloats, map, bar, sc0, (pos * K + k) * Th + sr0, va);
+    if (hint)
+      tma_load_box_hint(stage + (size_t)va * kBoxFloats, map, bar, sc0, (pos * K + k) * Th + sr0, va, policy);
+    else
+      tma_load_box(stage + (size_t)va * kBoxFloats, map, bar, sc0, (pos * K + k) * Th + sr0, va);
   }
 }
 
@@ -949,12 +997,12 @@ __device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) 
 }
 
 // LINEAR: the reduction is MEAN or SUM (no per-element transform): keeps the switch out of the inner loop
-template <int TTA, bool LINEAR, int MAXB>
-__global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
-                                                                      int nblocks) {
+template <int TTA, bool LINEAR, int MAXB, bool DEEP>
+__global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
+                                                                                 int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
-  constexpr int STAGES = tma_stages(NV);
+  constexpr int STAGES = tma_stages(NV, DEEP);
   // Boxes must be 1024-byte aligned for the 128-byte swizzle atom. This kernel has no static shared memory, so
   // the dynamic window starts at the (1024-aligned) base of the CTA's shared memory; checked below. No integer
   // round trips on the pointers: the compiler must keep them in the shared address space (LDS, not generic LD).
@@ -980,6 +1028,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
     // ------------------------------ producer: one lane feeds the ring ------------------------------
     if (lane == 0) {
       int it = 0;
+      const bool hint = (a.debug & 8) != 0;
+      const uint64_t policy = hint ? l2_evict_first_policy() : 0ull;
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const BlockWork w = block_work(a, blk);
         for (int k = 0; k < a.K; ++k) {
@@ -1000,7 +1050,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) merge_all_tma_kernel(MergeAllA
               mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
               const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
               tma_issue_views<V::packed, NV>(boxes + (size_t)s * NV * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi], &full[s], pos,
-                                             a.K, k, g.Th, g.Tw, i0, j0);
+                                             a.K, k, g.Th, g.Tw, i0, j0, hint, policy);
               ++it;
             }
           }
@@ -1253,6 +1303,15 @@ static inline bool tb_force_generic_merge() {
   return v && v[0] == '1';
 }
 
+static inline int slice_variant() {
+  const char* v = getenv("TB200_SLICE_VARIANT");
+  return v ? atoi(v) : 3;  // 6 CTAs/SM + streaming stores (measured best on cfg2: 1.60 ms vs 1.67-1.75 ms)
+}
+static inline int merge_variant() {
+  const char* v = getenv("TB200_MERGE_VARIANT");
+  return v ? atoi(v) : 1;  // deep ring, 1 CTA/SM (measured on cfg2: 2.17 ms vs 2.30 ms for 2 CTAs x 3 stages)
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace tb
@@ -1305,22 +1364,28 @@ static bool make_pred_tensor_map(const float* base, int b, int K, int Th, int Tw
 
 constexpr int kMaxTmaBatches = 192;  // 192 x 128 B of tensor maps = 24 KB of kernel parameters (limit 32 KB)
 
-template <int TTA, bool LINEAR, int MAXB>
-static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
+template <int TTA, bool LINEAR, int MAXB, bool DEEP>
+static cudaError_t launch_merge_all_tma_impl2(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
-  const size_t smem = tma_smem_bytes(NV);
+  const size_t smem = tma_smem_bytes(NV, DEEP);
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR, MAXB>, kTmaThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP>, kTmaThreads, smem);
     if (e != cudaSuccess) return e;
     ctas_per_sm = n > 0 ? n : 1;
   }
   const int grid = std::min(nblocks, sm_count() * ctas_per_sm);  // persistent: one resident wave
-  merge_all_tma_kernel<TTA, LINEAR, MAXB><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
+  merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
   return cudaGetLastError();
+}
+
+template <int TTA, bool LINEAR, int MAXB>
+static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
+  if (merge_variant() & 1) return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, true>(a, maps, nblocks, s);
+  return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, false>(a, maps, nblocks, s);
 }
 
 template <int TTA, int MAXB>
@@ -1426,8 +1491,17 @@ int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, i
   cudaStream_t s = (cudaStream_t)stream;
 #define TB_SLICE(SrcT)                                                                   \
   do {                                                                                   \
-    if (fast) {                                                                          \
-      TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a)); \
+    if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out)) {                         \
+      const long long work = (long long)n * Th * (Tw / 4);                               \
+      const int g = (int)std::min<long long>((work + kThreads - 1) / kThreads, (long long)sm_count() * 16); \
+      slice_plain_kernel<SrcT><<<g, kThreads, 0, s>>>(a);                                \
+    } else if (fast) {                                                                   \
+      switch (slice_variant()) {                                                         \
+        case 1: TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_, 1><<<(unsigned)blocks, kThreads, 0, s>>>(a)); break; \
+        case 2: TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_, 2><<<(unsigned)blocks, kThreads, 0, s>>>(a)); break; \
+        case 3: TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_, 3><<<(unsigned)blocks, kThreads, 0, s>>>(a)); break; \
+        default: TB_DISPATCH_TTA(tta, slice_augment_fast_kernel<SrcT, TTA_, 0><<<(unsigned)blocks, kThreads, 0, s>>>(a)); break; \
+      }                                                                                  \
     } else if (vec)                                                                      \
       slice_augment_kernel<SrcT, true><<<(unsigned)blocks, kThreads, 0, s>>>(a);         \
     else                                                                                 \
@@ -1697,6 +1771,7 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   {
     const char* dbg = getenv("TB200_TMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
+    if (merge_variant() & 2) a.debug |= 8;
   }
   // block window: rows from floor(y0/BS) to ceil(y1/BS); columns cover the crop (or the whole canvas when raw)
   const int xa = raw ? 0 : left, xb = raw ? Wp : left + W;
@@ -1772,6 +1847,7 @@ int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int
   {
     const char* dbg = getenv("TB200_TMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
+    if (merge_variant() & 2) a.debug |= 8;
   }
   a.first_tile = first_tile; a.batch_tiles = batch_tiles; a.covered_tiles = (int)covered;
   const int xa = raw ? 0 : left, xb = raw ? Wp : left + W;
