@@ -24,12 +24,13 @@ constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kBoxFloats = 32 * 32;
 constexpr int kBoxBytes = kBoxFloats * 4;
 
-// DEEP = one CTA per SM with a ring that fills the whole 227 KB of shared memory (7 x 32 KB for 8 views)
+// DEEP = one CTA per SM with a ring that fills (almost) the whole 227 KB of shared memory whatever the view count
+// (7 x 32 KB for 8 views ... 54 x 4 KB for a single view): bytes in flight per SM are what bound this kernel.
 __host__ __device__ constexpr int tma_stages(int views, bool deep = false) {
-  return deep ? (views >= 8 ? 7 : (views >= 3 ? 14 : 16)) : (views >= 8 ? 3 : (views >= 3 ? 6 : 10));
+  return deep ? (54 / views < 7 ? 7 : 54 / views) : (views >= 8 ? 3 : (views >= 3 ? 6 : 10));
 }
 __host__ __device__ constexpr size_t tma_smem_bytes(int views, bool deep = false) {
-  return (size_t)tma_stages(views, deep) * views * kBoxBytes + 2 * 16 * sizeof(uint64_t);
+  return (size_t)tma_stages(views, deep) * views * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) + 64;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

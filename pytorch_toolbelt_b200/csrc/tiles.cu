@@ -529,15 +529,13 @@ __global__ void __launch_bounds__(kThreads, (VAR & 1) ? 6 : 1) slice_augment_fas
 template <typename SrcT>
 __global__ void __launch_bounds__(kThreads) slice_plain_kernel(SliceArgs a) {
   const int groups_per_row = a.Tw >> 2;  // host guarantees Tw % 4 == 0
-  const long long per_tile = (long long)a.Th * groups_per_row;
-  const long long total = per_tile * a.n;
+  const int per_tile = a.Th * groups_per_row;
+  const int t = blockIdx.y;
   const SrcT* img = static_cast<const SrcT*>(a.img);
   const size_t plane = (size_t)a.Th * a.Tw;
-  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-    const int t = (int)(idx / per_tile);
-    const int rem = (int)(idx - (long long)t * per_tile);
+  const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+  for (int rem = blockIdx.x * kThreads + threadIdx.x; rem < per_tile; rem += gridDim.x * kThreads) {
     const int i = rem / groups_per_row, j = (rem - i * groups_per_row) << 2;
-    const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
     const int gy = y0 + i, gx = x0 + j;
     const bool interior = gy >= 0 && gy < a.H && gx >= 0 && gx + 3 < a.W;
     const int sy = interior ? gy : border_remap(gy, 0, a.H, a.border);
@@ -1491,9 +1489,9 @@ int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, i
   cudaStream_t s = (cudaStream_t)stream;
 #define TB_SLICE(SrcT)                                                                   \
   do {                                                                                   \
-    if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out)) {                         \
-      const long long work = (long long)n * Th * (Tw / 4);                               \
-      const int g = (int)std::min<long long>((work + kThreads - 1) / kThreads, (long long)sm_count() * 16); \
+    if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out) && n <= 65535) {           \
+      const int work = Th * (Tw / 4);                                                    \
+      dim3 g((unsigned)std::min((work + kThreads - 1) / kThreads, 64), (unsigned)n);     \
       slice_plain_kernel<SrcT><<<g, kThreads, 0, s>>>(a);                                \
     } else if (fast) {                                                                   \
       switch (slice_variant()) {                                                         \
