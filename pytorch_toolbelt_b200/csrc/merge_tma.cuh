@@ -20,7 +20,8 @@
 namespace tb {
 
 constexpr int kTmaConsumerWarps = 8;
-constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;  // + 1 producer warp
+constexpr int kTmaProducerWarps = 4;  // one elected lane each; producer p feeds the stages with (it % 4 == p)
+constexpr int kTmaThreads = (kTmaConsumerWarps + kTmaProducerWarps) * 32;
 constexpr int kBoxFloats = 32 * 32;
 constexpr int kBoxBytes = kBoxFloats * 4;
 

@@ -1022,8 +1022,9 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   }
   __syncthreads();
 
-  if (warp == kTmaConsumerWarps) {
-    // ------------------------------ producer: one lane feeds the ring ------------------------------
+  if (warp >= kTmaConsumerWarps) {
+    // ------------------------------ producers: one lane per producer warp feeds every 4th stage ------------------------------
+    const int prod = warp - kTmaConsumerWarps;
     if (lane == 0) {
       int it = 0;
       const bool hint = (a.debug & 8) != 0;
@@ -1036,6 +1037,10 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
               const int t = r * g.nx + c;
               const int rel = t - a.first_tile;
               if (rel < 0 || rel >= a.covered_tiles) continue;  // tile not resident (band mode): uniform decision
+              if ((it % kTmaProducerWarps) != prod) {  // another producer warp owns this stage
+                ++it;
+                continue;
+              }
               const int bi = rel / a.batch_tiles, pos = rel - bi * a.batch_tiles;
               const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
               const int s = it % ring;
@@ -1177,13 +1182,18 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
   __syncthreads();
   const int per_tile = a.nbx * a.nby;
 
-  if (warp == kTmaConsumerWarps) {
+  if (warp >= kTmaConsumerWarps) {
+    const int prod = warp - kTmaConsumerWarps;
     if (lane == 0) {
       int it = 0;
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int t = blk / per_tile, rem = blk - t * per_tile;
         const int i0 = (rem / a.nbx) * BS, j0 = (rem % a.nbx) * BS;
         for (int k = 0; k < a.K; ++k) {
+          if ((it % kTmaProducerWarps) != prod) {
+            ++it;
+            continue;
+          }
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
