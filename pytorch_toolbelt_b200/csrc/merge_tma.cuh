@@ -25,13 +25,17 @@ constexpr int kTmaThreads = (kTmaConsumerWarps + kTmaProducerWarps) * 32;
 constexpr int kBoxFloats = 32 * 32;
 constexpr int kBoxBytes = kBoxFloats * 4;
 
-// DEEP = one CTA per SM with a ring that fills (almost) the whole 227 KB of shared memory whatever the view count
-// (7 x 32 KB for 8 views ... 54 x 4 KB for a single view): bytes in flight per SM are what bound this kernel.
+// A stage holds up to tma_group(views) work items (covering tiles of one canvas block in the merge, channels of one
+// tile patch in the de-augment), each with all its views: 6-8 boxes = 24-32 KB per stage whatever the TTA group, so
+// that few-view configurations move as many bytes per barrier round trip as D4 does.
+__host__ __device__ constexpr int tma_group(int views) { return views >= 8 ? 1 : 8 / views; }
+__host__ __device__ constexpr int tma_stage_boxes(int views) { return tma_group(views) * views; }
+// DEEP = one CTA per SM with a ring that fills the 227 KB of shared memory (7 x 32 KB); else 2 CTAs x 3 stages.
 __host__ __device__ constexpr int tma_stages(int views, bool deep = false) {
-  return deep ? (54 / views < 7 ? 7 : 54 / views) : (views >= 8 ? 3 : (views >= 3 ? 6 : 10));
+  return (deep ? 56 : 24) / tma_stage_boxes(views);
 }
 __host__ __device__ constexpr size_t tma_smem_bytes(int views, bool deep = false) {
-  return (size_t)tma_stages(views, deep) * views * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) + 64;
+  return (size_t)tma_stages(views, deep) * tma_stage_boxes(views) * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) + 64;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -528,34 +528,41 @@ __global__ void __launch_bounds__(kThreads, (VAR & 1) ? 6 : 1) slice_augment_fas
 // ------------------------------------------------------------------------------------------------
 template <typename SrcT>
 __global__ void __launch_bounds__(kThreads) slice_plain_kernel(SliceArgs a) {
-  const int groups_per_row = a.Tw >> 2;  // host guarantees Tw % 4 == 0
-  const int per_tile = a.Th * groups_per_row;
+  // blockIdx.y = tile, blockIdx.x = band of rows; a thread keeps its 4 columns and walks down the rows of the band,
+  // so the column border remap is computed once per thread and a row costs one remap + C*4 loads + C stores.
+  const int groups = a.Tw >> 2;                 // host guarantees Tw % 4 == 0
+  const int gpt = min(groups, kThreads);        // column groups handled side by side
+  const int rsub = threadIdx.x / gpt, rstep = kThreads / gpt;
   const int t = blockIdx.y;
   const SrcT* img = static_cast<const SrcT*>(a.img);
   const size_t plane = (size_t)a.Th * a.Tw;
   const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
-  for (int rem = blockIdx.x * kThreads + threadIdx.x; rem < per_tile; rem += gridDim.x * kThreads) {
-    const int i = rem / groups_per_row, j = (rem - i * groups_per_row) << 2;
-    const int gy = y0 + i, gx = x0 + j;
-    const bool interior = gy >= 0 && gy < a.H && gx >= 0 && gx + 3 < a.W;
-    const int sy = interior ? gy : border_remap(gy, 0, a.H, a.border);
+  const int rows_per_block = (a.Th + gridDim.x - 1) / gridDim.x;
+  const int i_begin = blockIdx.x * rows_per_block, i_end = min(a.Th, i_begin + rows_per_block);
+  float* out_tile = a.out + (size_t)t * a.C * plane;
+  for (int cg = threadIdx.x % gpt; cg < groups; cg += gpt) {
+    const int j = cg << 2;
     int sx[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) sx[e] = interior ? gx + e : border_remap(gx + e, 0, a.W, a.border);
-    float* o = a.out + (size_t)t * a.C * plane + (size_t)i * a.Tw + j;
-    for (int c = 0; c < a.C; ++c) {
-      float v[4];
+    for (int e = 0; e < 4; ++e) sx[e] = border_remap(x0 + j + e, 0, a.W, a.border);
+    if (rsub >= rstep) continue;
+    for (int i = i_begin + rsub; i < i_end; i += rstep) {
+      const int sy = border_remap(y0 + i, 0, a.H, a.border);
+      float* o = out_tile + (size_t)i * a.Tw + j;
+      for (int c = 0; c < a.C; ++c) {
+        float v[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (sy < 0 || sx[e] < 0)
-          v[e] = c < 4 ? a.bval[c] : 0.f;
-        else if (a.layout == TB_HWC)
-          v[e] = to_f32(img[((size_t)sy * a.W + sx[e]) * a.C + c]);
-        else
-          v[e] = to_f32(img[((size_t)c * a.H + sy) * a.W + sx[e]]);
-        if (a.has_affine && c < 8) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[c]), a.bias[c]);
+        for (int e = 0; e < 4; ++e) {
+          if (sy < 0 || sx[e] < 0)
+            v[e] = c < 4 ? a.bval[c] : 0.f;
+          else if (a.layout == TB_HWC)
+            v[e] = to_f32(img[((size_t)sy * a.W + sx[e]) * a.C + c]);
+          else
+            v[e] = to_f32(img[((size_t)c * a.H + sy) * a.W + sx[e]]);
+          if (a.has_affine && c < 8) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[c]), a.bias[c]);
+        }
+        __stcs(reinterpret_cast<float4*>(o + (size_t)c * plane), make_float4(v[0], v[1], v[2], v[3]));
       }
-      __stcs(reinterpret_cast<float4*>(o + (size_t)c * plane), make_float4(v[0], v[1], v[2], v[3]));
     }
   }
 }
@@ -994,19 +1001,32 @@ __device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) 
   return w;
 }
 
+// Number of resident covering tiles of a block (identical on the producer and the consumer side).
+__device__ __forceinline__ int block_tile_count(const MergeAllArgs& a, const BlockWork& w) {
+  int nt = 0;
+  for (int r = w.ra; r <= w.rb; ++r)
+    for (int c = w.ca; c <= w.cb; ++c) {
+      const int rel = r * a.grid.nx + c - a.first_tile;
+      nt += (rel >= 0 && rel < a.covered_tiles) ? 1 : 0;
+    }
+  return nt;
+}
+
 // LINEAR: the reduction is MEAN or SUM (no per-element transform): keeps the switch out of the inner loop
 template <int TTA, bool LINEAR, int MAXB, bool DEEP>
 __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
                                                                                  int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
+  constexpr int G = tma_group(NV);         // covering tiles per stage
+  constexpr int SB = tma_stage_boxes(NV);  // boxes per stage
   constexpr int STAGES = tma_stages(NV, DEEP);
   // Boxes must be 1024-byte aligned for the 128-byte swizzle atom. This kernel has no static shared memory, so
   // the dynamic window starts at the (1024-aligned) base of the CTA's shared memory; checked below. No integer
   // round trips on the pointers: the compiler must keep them in the shared address space (LDS, not generic LD).
   extern __shared__ __align__(1024) float smem_boxes[];
   float* boxes = smem_boxes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * NV * kBoxFloats);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * SB * kBoxFloats);
   uint64_t* empty = full + STAGES;
   if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
 
@@ -1023,7 +1043,7 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   __syncthreads();
 
   if (warp >= kTmaConsumerWarps) {
-    // ------------------------------ producers: one lane per producer warp feeds every 4th stage ------------------------------
+    // ---------------- producers: one lane per producer warp feeds every kTmaProducerWarps-th stage ----------------
     const int prod = warp - kTmaConsumerWarps;
     if (lane == 0) {
       int it = 0;
@@ -1031,30 +1051,36 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
       const uint64_t policy = hint ? l2_evict_first_policy() : 0ull;
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const BlockWork w = block_work(a, blk);
+        const int nt = block_tile_count(a, w);
         for (int k = 0; k < a.K; ++k) {
+          int idx = 0, s = 0;
+          bool mine = false;
           for (int r = w.ra; r <= w.rb; ++r) {
             for (int c = w.ca; c <= w.cb; ++c) {
-              const int t = r * g.nx + c;
-              const int rel = t - a.first_tile;
-              if (rel < 0 || rel >= a.covered_tiles) continue;  // tile not resident (band mode): uniform decision
-              if ((it % kTmaProducerWarps) != prod) {  // another producer warp owns this stage
-                ++it;
-                continue;
+              const int rel = r * g.nx + c - a.first_tile;
+              if (rel < 0 || rel >= a.covered_tiles) continue;  // tile not resident (band mode)
+              const int gi = idx % G;
+              if (gi == 0) {  // open a stage
+                mine = (it % kTmaProducerWarps) == prod;
+                if (mine) {
+                  s = it % STAGES;
+                  const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                  mbar_wait(&empty[s], ph ^ 1u);
+                  // The consumers read this slot through the generic proxy; the TMA refill writes it through the
+                  // async proxy. The mbarrier orders the threads, not the proxies: without this fence the refill can
+                  // overtake reads that are still in flight (observed as a nondeterministic WAR race).
+                  fence_proxy_async();
+                  mbar_arrive_expect_tx(&full[s], (uint32_t)min(G, nt - idx) * NV * kBoxBytes);
+                }
               }
-              const int bi = rel / a.batch_tiles, pos = rel - bi * a.batch_tiles;
-              const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
-              const int s = it % ring;
-              const uint32_t ph = (uint32_t)(it / ring) & 1u;
-              mbar_wait(&empty[s], ph ^ 1u);
-              // The consumers read this slot through the generic proxy; the TMA refill writes it through the
-              // async proxy. The mbarrier orders the threads, not the proxies: without this fence the refill can
-              // overtake reads that are still in flight (observed as a nondeterministic WAR race with 1-view stages).
-              fence_proxy_async();
-              mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
-              const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
-              tma_issue_views<V::packed, NV>(boxes + (size_t)s * NV * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi], &full[s], pos,
-                                             a.K, k, g.Th, g.Tw, i0, j0, hint, policy);
-              ++it;
+              if (mine) {
+                const int bi = rel / a.batch_tiles, pos = rel - bi * a.batch_tiles;
+                const int i0 = w.Y0 - r * g.Sy, j0 = w.X0 - c * g.Sx;  // block origin inside the tile
+                tma_issue_views<V::packed, NV>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, &maps.m[MAXB == 1 ? 0 : bi],
+                                               &full[s], pos, a.K, k, g.Th, g.Tw, i0, j0, hint, policy);
+              }
+              ++idx;
+              if (gi == G - 1 || idx == nt) ++it;  // stage closed
             }
           }
         }
@@ -1064,10 +1090,7 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   }
 
   // ------------------------------ consumers ------------------------------
-  // Each thread owns 4 consecutive columns (one 16-byte chunk) of one row of the 32x32 block:
-  //   row  li = 8*(warp&3) + (lane&7),  chunk cq = 4*(warp>>2) + (lane>>3)  (columns 4*cq .. 4*cq+3).
-  // A quarter-warp therefore touches 8 rows with distinct (row & 7): with the 128-byte swizzle its eight
-  // 16-byte chunks land in 8 distinct bank groups, so the LDS.128 of non-transposing views are conflict-free.
+  // Each thread owns 4 consecutive columns (one 16-byte chunk) of one row of the 32x32 block (TmaOffsets).
   const int li = 8 * (warp & 3) + (lane & 7);
   const int cq = 4 * (warp >> 2) + (lane >> 3);
   const int lj = 4 * cq;
@@ -1079,6 +1102,7 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   int it = 0;
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const BlockWork w = block_work(a, blk);
+    const int nt = block_tile_count(a, w);
     const int y = w.Y0 + li;
     const bool y_ok = (y >= a.y0 && y < a.y1);
     for (int k = 0; k < a.K; ++k) {
@@ -1090,14 +1114,12 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
         acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
         den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
+      int idx = 0, s = 0;
       for (int r = w.ra; r <= w.rb; ++r) {
         for (int c = w.ca; c <= w.cb; ++c) {
-          const int t = r * g.nx + c;
-          const int rel = t - a.first_tile;
+          const int rel = r * g.nx + c - a.first_tile;
           if (rel < 0 || rel >= a.covered_tiles) continue;
-          const int ring = (a.debug & 4) ? min(STAGES, 3) : STAGES;
-          const int s = it % ring;
-          const uint32_t ph = (uint32_t)(it / ring) & 1u;
+          const int gi = idx % G;
           // weights first: their latency overlaps the wait for the stage
           const int ti = w.Y0 - r * g.Sy + li, tj = w.X0 - c * g.Sx + lj;
           float wt[4];
@@ -1108,19 +1130,23 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
 #pragma unroll
             for (int e = 0; e < 4; ++e) wt[e] = weight_at<float>(a.w, ti, tj + e);
           }
-          mbar_wait(&full[s], ph);
-          const float* st = boxes + (size_t)s * NV * kBoxFloats;
+          if (gi == 0) {
+            s = it % STAGES;
+            mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+          }
           float v[4];
-          offs.template reduce<LINEAR>(st, a.red, v);
-          if (a.debug & 1) asm volatile("bar.sync 1, 256;" ::: "memory");  // all consumer warps done reading
-          mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
+          offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
+          ++idx;
+          if (gi == G - 1 || idx == nt) {  // last tile of the stage: hand the slot back
+            mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
+            ++it;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float r4 = tma_post<LINEAR, NV>(a.red, v[e]);
             acc[e] = add_rn(acc[e], mul_rn(r4, wt[e]));
             den[e] = add_rn(den[e], wt[e]);
           }
-          ++it;
         }
       }
       if (!y_ok) continue;
@@ -1165,10 +1191,12 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
                                                                        int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
+  constexpr int G = tma_group(NV);  // channels per stage
+  constexpr int SB = tma_stage_boxes(NV);
   constexpr int STAGES = tma_stages(NV);
   extern __shared__ __align__(1024) float smem_boxes[];
   float* boxes = smem_boxes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * NV * kBoxFloats);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * SB * kBoxFloats);
   uint64_t* empty = full + STAGES;
   if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1189,18 +1217,16 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int t = blk / per_tile, rem = blk - t * per_tile;
         const int i0 = (rem / a.nbx) * BS, j0 = (rem % a.nbx) * BS;
-        for (int k = 0; k < a.K; ++k) {
-          if ((it % kTmaProducerWarps) != prod) {
-            ++it;
-            continue;
-          }
+        for (int k0 = 0; k0 < a.K; k0 += G, ++it) {
+          if ((it % kTmaProducerWarps) != prod) continue;
           const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
           fence_proxy_async();  // generic-proxy reads of the slot before the async-proxy refill (see 7b)
-          mbar_arrive_expect_tx(&full[s], NV * kBoxBytes);
-          tma_issue_views<V::packed, NV>(boxes + (size_t)s * NV * kBoxFloats, &maps.m[0], &full[s], t, a.K, k, a.Th, a.Tw, i0, j0);
-          ++it;
+          const int cnt = min(G, a.K - k0);
+          mbar_arrive_expect_tx(&full[s], (uint32_t)cnt * NV * kBoxBytes);
+          for (int gi = 0; gi < cnt; ++gi)
+            tma_issue_views<V::packed, NV>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, &maps.m[0], &full[s], t, a.K, k0 + gi,
+                                           a.Th, a.Tw, i0, j0);
         }
       }
     }
@@ -1233,30 +1259,32 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
       cpix = (size_t)(y0 + i) * a.Wp + (x0 + j);
       vec_ok = ((x0 & 3) == 0) && ((a.Wp & 3) == 0);
     }
-    for (int k = 0; k < a.K; ++k) {
+    for (int k0 = 0; k0 < a.K; k0 += G, ++it) {
       const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(&full[s], ph);
-      float v[4];
-      offs.template reduce<LINEAR>(boxes + (size_t)s * NV * kBoxFloats, a.red, v);
-      mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
+      const int cnt = min(G, a.K - k0);
+      mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+      for (int gi = 0; gi < cnt; ++gi) {
+        const int k = k0 + gi;
+        float v[4];
+        offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
+        if (gi == cnt - 1) mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = tma_post<LINEAR, NV>(a.red, v[e]);
-      if (SCATTER) {
+        for (int e = 0; e < 4; ++e) v[e] = tma_post<LINEAR, NV>(a.red, v[e]);
+        if (SCATTER) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = mul_rn(v[e], wt[e]);
-        float* dst = a.image + (size_t)k * a.Hp * a.Wp + cpix;
-        if (vec_ok) {
-          red_add4(dst, v);
+          for (int e = 0; e < 4; ++e) v[e] = mul_rn(v[e], wt[e]);
+          float* dst = a.image + (size_t)k * a.Hp * a.Wp + cpix;
+          if (vec_ok) {
+            red_add4(dst, v);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) red_add1(dst + e, v[e]);
+          }
         } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) red_add1(dst + e, v[e]);
+          __stcs(reinterpret_cast<float4*>(a.out + ((size_t)t * a.K + k) * plane + (size_t)i * a.Tw + j),
+                 make_float4(v[0], v[1], v[2], v[3]));
         }
-      } else {
-        __stcs(reinterpret_cast<float4*>(a.out + ((size_t)t * a.K + k) * plane + (size_t)i * a.Tw + j),
-               make_float4(v[0], v[1], v[2], v[3]));
       }
-      ++it;
     }
     if (SCATTER && a.norm) {
       float* dst = a.norm + cpix;
@@ -1500,8 +1528,8 @@ int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, i
 #define TB_SLICE(SrcT)                                                                   \
   do {                                                                                   \
     if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out) && n <= 65535) {           \
-      const int work = Th * (Tw / 4);                                                    \
-      dim3 g((unsigned)std::min((work + kThreads - 1) / kThreads, 64), (unsigned)n);     \
+      const int bands = std::max(1, std::min(Th / 8, std::max(1, (sm_count() * 8 + n - 1) / n))); \
+      dim3 g((unsigned)bands, (unsigned)n);                                              \
       slice_plain_kernel<SrcT><<<g, kThreads, 0, s>>>(a);                                \
     } else if (fast) {                                                                   \
       switch (slice_variant()) {                                                         \
