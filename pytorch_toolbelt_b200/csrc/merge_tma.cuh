@@ -53,8 +53,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Warp-level stage release: every lane's loaded values are consumed by the asm (so the loads have completed), the
 // warp converges, then one lane arrives.
+// The slot was read through the generic proxy and will be refilled through the async proxy (TMA): the reading threads
+// themselves issue the cross-proxy fence, then the warp converges and one lane arrives. (Putting the fence in the
+// producer instead also hides the race, but there it waits for the producer's own outstanding TMA loads and
+// serialises the whole ring to one stage per DRAM round trip.)
 __device__ __forceinline__ void mbar_release_after(uint64_t* bar, float a, float b, float c, float d, bool elected) {
   asm volatile("" ::"f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  fence_proxy_async();
   __syncwarp();
   if (elected) mbar_arrive(bar);
 }

@@ -1066,10 +1066,7 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
                   s = it % STAGES;
                   const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                   mbar_wait(&empty[s], ph ^ 1u);
-                  // The consumers read this slot through the generic proxy; the TMA refill writes it through the
-                  // async proxy. The mbarrier orders the threads, not the proxies: without this fence the refill can
-                  // overtake reads that are still in flight (observed as a nondeterministic WAR race).
-                  fence_proxy_async();
+                  if (a.debug & 2) fence_proxy_async();  // (A/B switch: producer-side fence, see mbar_release_after)
                   mbar_arrive_expect_tx(&full[s], (uint32_t)min(G, nt - idx) * NV * kBoxBytes);
                 }
               }
@@ -1221,7 +1218,6 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
           if ((it % kTmaProducerWarps) != prod) continue;
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-          fence_proxy_async();  // generic-proxy reads of the slot before the async-proxy refill (see 7b)
           const int cnt = min(G, a.K - k0);
           mbar_arrive_expect_tx(&full[s], (uint32_t)cnt * NV * kBoxBytes);
           for (int gi = 0; gi < cnt; ++gi)
