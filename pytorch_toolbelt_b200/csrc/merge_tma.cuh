@@ -32,10 +32,11 @@ __host__ __device__ constexpr int tma_group(int views) { return views >= 8 ? 1 :
 __host__ __device__ constexpr int tma_stage_boxes(int views) { return tma_group(views) * views; }
 // DEEP = one CTA per SM with a ring that fills the 227 KB of shared memory (7 x 32 KB); else 2 CTAs x 3 stages.
 __host__ __device__ constexpr int tma_stages(int views, bool deep = false) {
-  return (deep ? 56 : 24) / tma_stage_boxes(views);
+  return (deep ? 55 : 24) / tma_stage_boxes(views);  // 55: 6 x 32 KB + slack for the in-kernel alignment
 }
 __host__ __device__ constexpr size_t tma_smem_bytes(int views, bool deep = false) {
-  return (size_t)tma_stages(views, deep) * tma_stage_boxes(views) * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) + 64;
+  return (size_t)tma_stages(views, deep) * tma_stage_boxes(views) * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) +
+         1024 /* the CTA's dynamic window is not always 1024-aligned: aligned in-kernel */ + 64;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -549,6 +549,20 @@ __global__ void __launch_bounds__(kThreads) slice_plain_kernel(SliceArgs a) {
     for (int i = i_begin + rsub; i < i_end; i += rstep) {
       const int sy = border_remap(y0 + i, 0, a.H, a.border);
       float* o = out_tile + (size_t)i * a.Tw + j;
+      if (sizeof(SrcT) == 1 && a.C == 1 && sy >= 0 && sx[0] >= 0 && sx[3] == sx[0] + 3) {
+        // 4 consecutive bytes of one row: a single 32-bit load when the address allows it
+        const size_t off = (size_t)sy * a.W + sx[0];
+        if ((off & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 3) == 0)) {
+          const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(img) + off));
+          float v[4] = {(float)q.x, (float)q.y, (float)q.z, (float)q.w};
+          if (a.has_affine) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[0]), a.bias[0]);
+          }
+          __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+          continue;
+        }
+      }
       for (int c = 0; c < a.C; ++c) {
         float v[4];
 #pragma unroll
@@ -1001,6 +1015,30 @@ __device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) 
   return w;
 }
 
+// Iterator over the resident covering tiles of a block, row-major (the reference's accumulation order).
+struct TileIter {
+  int r, c;
+};
+__device__ __forceinline__ bool tile_resident(const MergeAllArgs& a, int r, int c) {
+  const int rel = r * a.grid.nx + c - a.first_tile;
+  return rel >= 0 && rel < a.covered_tiles;
+}
+__device__ __forceinline__ void tile_iter_settle(const MergeAllArgs& a, const BlockWork& w, TileIter& p) {
+  while (p.r <= w.rb && !tile_resident(a, p.r, p.c)) {
+    if (++p.c > w.cb) {
+      p.c = w.ca;
+      ++p.r;
+    }
+  }
+}
+__device__ __forceinline__ void tile_iter_next(const MergeAllArgs& a, const BlockWork& w, TileIter& p) {
+  if (++p.c > w.cb) {
+    p.c = w.ca;
+    ++p.r;
+  }
+  tile_iter_settle(a, w, p);
+}
+
 // Number of resident covering tiles of a block (identical on the producer and the consumer side).
 __device__ __forceinline__ int block_tile_count(const MergeAllArgs& a, const BlockWork& w) {
   int nt = 0;
@@ -1024,11 +1062,13 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   // Boxes must be 1024-byte aligned for the 128-byte swizzle atom. This kernel has no static shared memory, so
   // the dynamic window starts at the (1024-aligned) base of the CTA's shared memory; checked below. No integer
   // round trips on the pointers: the compiler must keep them in the shared address space (LDS, not generic LD).
-  extern __shared__ __align__(1024) float smem_boxes[];
-  float* boxes = smem_boxes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * SB * kBoxFloats);
+  extern __shared__ __align__(16) float smem_boxes[];
+  // 1024-byte alignment for the 128-byte swizzle atom, computed on the SHARED address (the window of a CTA is not
+  // always 1024-aligned when other kernels' CTAs are resident) and applied as an element offset, so the pointer
+  // provably stays in the shared address space (LDS, not generic LD).
+  float* boxes = smem_boxes + (((1024u - (smem_u32(smem_boxes) & 1023u)) & 1023u) >> 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(boxes + STAGES * SB * kBoxFloats);
   uint64_t* empty = full + STAGES;
-  if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
 
   const tb_grid& g = a.grid;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1111,38 +1151,44 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
         acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
         den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
-      int idx = 0, s = 0;
-      for (int r = w.ra; r <= w.rb; ++r) {
-        for (int c = w.ca; c <= w.cb; ++c) {
-          const int rel = r * g.nx + c - a.first_tile;
-          if (rel < 0 || rel >= a.covered_tiles) continue;
-          const int gi = idx % G;
-          // weights first: their latency overlaps the wait for the stage
-          const int ti = w.Y0 - r * g.Sy + li, tj = w.X0 - c * g.Sx + lj;
-          float wt[4];
-          if (a.w.kind == TB_W_TABLE) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)ti * g.Tw + tj));
-            wt[0] = w4.x; wt[1] = w4.y; wt[2] = w4.z; wt[3] = w4.w;
-          } else {
+      TileIter cur = {w.ra, w.ca};
+      tile_iter_settle(a, w, cur);
+      for (int g0 = 0; g0 < nt; g0 += G, ++it) {
+        const int cnt = min(G, nt - g0);
+        // the weights of ALL tiles of the stage first: their (L2) latencies overlap each other and the wait below
+        float wt[G][4];
+        {
+          TileIter p = cur;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) wt[e] = weight_at<float>(a.w, ti, tj + e);
-          }
-          if (gi == 0) {
-            s = it % STAGES;
-            mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
-          }
-          float v[4];
-          offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
-          ++idx;
-          if (gi == G - 1 || idx == nt) {  // last tile of the stage: hand the slot back
-            mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);
-            ++it;
-          }
+          for (int gi = 0; gi < G; ++gi) {
+            if (gi < cnt) {
+              const int ti = w.Y0 - p.r * g.Sy + li, tj = w.X0 - p.c * g.Sx + lj;
+              if (a.w.kind == TB_W_TABLE) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)ti * g.Tw + tj));
+                wt[gi][0] = w4.x; wt[gi][1] = w4.y; wt[gi][2] = w4.z; wt[gi][3] = w4.w;
+              } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float r4 = tma_post<LINEAR, NV>(a.red, v[e]);
-            acc[e] = add_rn(acc[e], mul_rn(r4, wt[e]));
-            den[e] = add_rn(den[e], wt[e]);
+                for (int e = 0; e < 4; ++e) wt[gi][e] = weight_at<float>(a.w, ti, tj + e);
+              }
+              tile_iter_next(a, w, p);
+            }
+          }
+          cur = p;
+        }
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          if (gi < cnt) {
+            float v[4];
+            offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
+            if (gi == cnt - 1) mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);  // slot back to the producers
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float r4 = tma_post<LINEAR, NV>(a.red, v[e]);
+              acc[e] = add_rn(acc[e], mul_rn(r4, wt[gi][e]));
+              den[e] = add_rn(den[e], wt[gi][e]);
+            }
           }
         }
       }
@@ -1191,11 +1237,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2) tile_deaug_tma_kernel(TileTmaA
   constexpr int G = tma_group(NV);  // channels per stage
   constexpr int SB = tma_stage_boxes(NV);
   constexpr int STAGES = tma_stages(NV);
-  extern __shared__ __align__(1024) float smem_boxes[];
-  float* boxes = smem_boxes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_boxes + STAGES * SB * kBoxFloats);
+  extern __shared__ __align__(16) float smem_boxes[];
+  // 1024-byte alignment for the 128-byte swizzle atom, computed on the SHARED address (the window of a CTA is not
+  // always 1024-aligned when other kernels' CTAs are resident) and applied as an element offset, so the pointer
+  // provably stays in the shared address space (LDS, not generic LD).
+  float* boxes = smem_boxes + (((1024u - (smem_u32(smem_boxes) & 1023u)) & 1023u) >> 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(boxes + STAGES * SB * kBoxFloats);
   uint64_t* empty = full + STAGES;
-  if (threadIdx.x == 0 && (smem_u32(smem_boxes) & 1023u)) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
