@@ -20,7 +20,10 @@
 namespace tb {
 
 constexpr int kTmaConsumerWarps = 8;
-constexpr int kTmaProducerWarps = 4;  // one elected lane each; producer p feeds the stages with (it % 4 == p)
+// One producer warp (one elected lane). More producers are NOT safe with a parity-based ring unless their count is
+// <= the ring depth: a producer that skips more than one ring revolution between its own waits aliases the mbarrier
+// phase parity (found by compute-sanitizer with 4 producers on the 3-stage ring) -- and they bought no speed.
+constexpr int kTmaProducerWarps = 1;
 constexpr int kTmaThreads = (kTmaConsumerWarps + kTmaProducerWarps) * 32;
 constexpr int kBoxFloats = 32 * 32;
 constexpr int kBoxBytes = kBoxFloats * 4;
