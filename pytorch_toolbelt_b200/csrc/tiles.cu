@@ -1389,7 +1389,7 @@ static inline int slice_variant() {
 }
 static inline int merge_variant() {
   const char* v = getenv("TB200_MERGE_VARIANT");
-  return v ? atoi(v) : 1;  // deep ring, 1 CTA/SM (measured on cfg2: 2.17 ms vs 2.30 ms for 2 CTAs x 3 stages)
+  return v ? atoi(v) : 0;  // bit1: L2 evict-first hint on the TMA loads (A/B switch; no measurable gain)
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -1464,8 +1464,8 @@ static cudaError_t launch_merge_all_tma_impl2(const MergeAllArgs& a, const TmaMa
 
 template <int TTA, bool LINEAR, int MAXB>
 static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
-  if (merge_variant() & 1) return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, true>(a, maps, nblocks, s);
-  return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, false>(a, maps, nblocks, s);
+  // always the deep ring (1 CTA/SM, ~200 KB of stages): measured 2.17 ms vs 2.30 ms for 2 CTAs x 3 stages on cfg2
+  return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, true>(a, maps, nblocks, s);
 }
 
 template <int TTA, int MAXB>
@@ -1869,7 +1869,9 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
-  if (al && pred && !grid->tile_slot && tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
+  const bool tiny_stages = (a.views.count * K) < 4;  // 1-2 boxes per block: barrier round trips dominate, plain loads win
+  if (al && pred && !grid->tile_slot && !tiny_stages &&
+      tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
     TmaMaps<1> maps;
     if (make_pred_tensor_map(pred, grid->n_slots, K, grid->Th, grid->Tw, a.views.count, &maps.m[0])) {
       a.first_tile = 0;

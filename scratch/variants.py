@@ -30,7 +30,7 @@ for v in ("0", "1", "2", "3"):
     ms = timed(lambda: eng.slice(image, out=aug))
     print("slice variant", v, round(ms, 4), "ms", "ok" if abs(aug.double().sum().item() - ref_aug_sum) == 0 else "MISMATCH", flush=True)
 os.environ["TB200_SLICE_VARIANT"] = "0"
-for v in ("0", "1", "2", "3"):
+for v in ("0", "2"):
     os.environ["TB200_MERGE_VARIANT"] = v
     ms = timed(lambda: eng.merge(pred, out=out))
     print("merge variant", v, round(ms, 4), "ms", "ok" if torch.equal(out, ref_out) else "MISMATCH", flush=True)
