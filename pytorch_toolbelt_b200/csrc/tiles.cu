@@ -838,6 +838,56 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
           den[e] = a.init_den[o + e];
         }
     }
+    if (V::count == 1 && ALIGNED) {
+      // Single view (no TTA): nothing to stage or reduce, so the only enemy is latency. Walk the covering tiles in
+      // chunks of four and issue all prediction and weight loads of a chunk before consuming any of them.
+      int r = ra, c = ca;
+      while (r <= rb) {
+        float pv[4][4], wv[4][4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          ok[u] = false;
+          if (r <= rb) {
+            const int t = r * g.nx + c;
+            const float* base = nullptr;
+            if (g.tile_ptr) {
+              base = g.tile_ptr[t];
+            } else {
+              const int slot = g.tile_slot ? __ldg(g.tile_slot + t) : t;
+              if (slot >= 0) base = a.pred + (size_t)slot * a.K * plane;
+            }
+            const int i = Y0 - r * g.Sy + li, j = X0 - c * g.Sx + 4 * lq;
+            if (base && i >= 0 && i < g.Th && j >= 0 && j + 3 < g.Tw) {
+              ok[u] = true;
+              ld_stream4(base + (size_t)k * plane + (size_t)i * g.Tw + j, pv[u]);
+              if (a.w.kind == TB_W_TABLE) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)i * g.Tw + j));
+                wv[u][0] = w4.x; wv[u][1] = w4.y; wv[u][2] = w4.z; wv[u][3] = w4.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) wv[u][e] = weight_at<float>(a.w, i, j + e);
+              }
+            }
+            if (++c > cb) {
+              c = ca;
+              ++r;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (ok[u]) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float val = red_post<float>(a.red, red_pre<float>(a.red, pv[u][e]), 1);
+              acc[e] = add_rn(acc[e], mul_rn(val, wv[u][e]));
+              den[e] = add_rn(den[e], wv[u][e]);
+            }
+          }
+        }
+      }
+    } else
     for (int r = ra; r <= rb; ++r) {
       for (int c = ca; c <= cb; ++c) {
         const int t = r * g.nx + c;
