@@ -33,9 +33,9 @@ constexpr int kBoxBytes = kBoxFloats * 4;
 // that few-view configurations move as many bytes per barrier round trip as D4 does.
 __host__ __device__ constexpr int tma_group(int views) { return views >= 8 ? 1 : 8 / views; }
 __host__ __device__ constexpr int tma_stage_boxes(int views) { return tma_group(views) * views; }
-// DEEP = one CTA per SM with a ring that fills the 227 KB of shared memory (7 x 32 KB); else 2 CTAs x 3 stages.
+// deep = one CTA per SM with a ring that fills the 227 KB of shared memory (7 x 32 KB); else 2 CTAs x 3 stages.
 __host__ __device__ constexpr int tma_stages(int views, bool deep = false) {
-  return (deep ? 55 : 24) / tma_stage_boxes(views);  // 55: 6 x 32 KB + slack for the in-kernel alignment
+  return (deep ? 56 : 24) / tma_stage_boxes(views);  // 7 x 32 KB + barriers + 1 KB alignment slack <= 227 KB
 }
 __host__ __device__ constexpr size_t tma_smem_bytes(int views, bool deep = false) {
   return (size_t)tma_stages(views, deep) * tma_stage_boxes(views) * kBoxBytes + 2 * (size_t)tma_stages(views, deep) * sizeof(uint64_t) +
@@ -61,9 +61,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // themselves issue the cross-proxy fence, then the warp converges and one lane arrives. (Putting the fence in the
 // producer instead also hides the race, but there it waits for the producer's own outstanding TMA loads and
 // serialises the whole ring to one stage per DRAM round trip.)
-__device__ __forceinline__ void mbar_release_after(uint64_t* bar, float a, float b, float c, float d, bool elected) {
+__device__ __forceinline__ void mbar_release_after(uint64_t* bar, float a, float b, float c, float d, bool elected,
+                                                   bool skip_fence = false) {
   asm volatile("" ::"f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-  fence_proxy_async();
+  if (!skip_fence) fence_proxy_async();
   __syncwarp();
   if (elected) mbar_arrive(bar);
 }

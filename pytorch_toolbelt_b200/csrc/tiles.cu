@@ -1101,45 +1101,50 @@ __device__ __forceinline__ int block_tile_count(const MergeAllArgs& a, const Blo
 }
 
 // LINEAR: the reduction is MEAN or SUM (no per-element transform): keeps the switch out of the inner loop
-template <int TTA, bool LINEAR, int MAXB, bool DEEP>
-__global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
-                                                                                 int nblocks) {
+// NG = independent pipelines ("virtual CTAs") inside the CTA: each has 8 consumer warps, one producer warp, its own
+// share of the stage ring and walks its own canvas blocks. NG = 2 doubles the warps available to hide the consumers'
+// fixed-latency stalls, which is what few-view stages (few bytes per barrier round trip) need; D4 keeps NG = 1 and the
+// deepest ring.
+template <int TTA, bool LINEAR, int MAXB, int NG>
+__global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(MergeAllArgs a, const __grid_constant__ TmaMaps<MAXB> maps,
+                                                                           int nblocks) {
   using V = Views<TTA>;
   constexpr int NV = V::count;
   constexpr int G = tma_group(NV);         // covering tiles per stage
   constexpr int SB = tma_stage_boxes(NV);  // boxes per stage
-  constexpr int STAGES = tma_stages(NV, DEEP);
-  // Boxes must be 1024-byte aligned for the 128-byte swizzle atom. This kernel has no static shared memory, so
-  // the dynamic window starts at the (1024-aligned) base of the CTA's shared memory; checked below. No integer
-  // round trips on the pointers: the compiler must keep them in the shared address space (LDS, not generic LD).
+  constexpr int STAGES = tma_stages(NV, true) / NG;  // per pipeline
   extern __shared__ __align__(16) float smem_boxes[];
   // 1024-byte alignment for the 128-byte swizzle atom, computed on the SHARED address (the window of a CTA is not
   // always 1024-aligned when other kernels' CTAs are resident) and applied as an element offset, so the pointer
   // provably stays in the shared address space (LDS, not generic LD).
-  float* boxes = smem_boxes + (((1024u - (smem_u32(smem_boxes) & 1023u)) & 1023u) >> 2);
-  uint64_t* full = reinterpret_cast<uint64_t*>(boxes + STAGES * SB * kBoxFloats);
-  uint64_t* empty = full + STAGES;
+  float* boxes_all = smem_boxes + (((1024u - (smem_u32(smem_boxes) & 1023u)) & 1023u) >> 2);
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(boxes_all + NG * STAGES * SB * kBoxFloats);
 
   const tb_grid& g = a.grid;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warps [0, 8*NG) consume (pipeline = warp / 8), warps [8*NG, 9*NG) produce
+  const bool is_producer = warp_all >= kTmaConsumerWarps * NG;
+  const int pipe = is_producer ? warp_all - kTmaConsumerWarps * NG : warp_all / kTmaConsumerWarps;
+  const int warp = is_producer ? kTmaConsumerWarps : warp_all % kTmaConsumerWarps;
+  float* boxes = boxes_all + (size_t)pipe * STAGES * SB * kBoxFloats;
+  uint64_t* full = bars_all + (size_t)pipe * 2 * STAGES;
+  uint64_t* empty = full + STAGES;
+  const int blk0 = blockIdx.x * NG + pipe, blk_step = gridDim.x * NG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kTmaConsumerWarps);
-    }
+    for (int s = 0; s < 2 * STAGES * NG; ++s) mbar_init(&bars_all[s], ((s / STAGES) & 1) ? kTmaConsumerWarps : 1);
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp >= kTmaConsumerWarps) {
-    // ---------------- producers: one lane per producer warp feeds every kTmaProducerWarps-th stage ----------------
-    const int prod = warp - kTmaConsumerWarps;
+  if (is_producer) {
+    // ---------------- producer of this pipeline: one elected lane feeds its ring ----------------
+    const int prod = 0;
     if (lane == 0) {
       int it = 0;
       const bool hint = (a.debug & 8) != 0;
       const uint64_t policy = hint ? l2_evict_first_policy() : 0ull;
-      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      for (int blk = blk0; blk < nblocks; blk += blk_step) {
         const BlockWork w = block_work(a, blk);
         const int nt = block_tile_count(a, w);
         for (int k = 0; k < a.K; ++k) {
@@ -1187,7 +1192,7 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
   offs.init(li, cq);
 
   int it = 0;
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  for (int blk = blk0; blk < nblocks; blk += blk_step) {
     const BlockWork w = block_work(a, blk);
     const int nt = block_tile_count(a, w);
     const int y = w.Y0 + li;
@@ -1232,7 +1237,8 @@ __global__ void __launch_bounds__(kTmaThreads, DEEP ? 1 : 2) merge_all_tma_kerne
           if (gi < cnt) {
             float v[4];
             offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
-            if (gi == cnt - 1) mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0);  // slot back to the producers
+            if (gi == cnt - 1)  // slot back to the producer (debug bit 16: timing-only switch that drops the proxy fence)
+              mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0, (a.debug & 16) != 0);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float r4 = tma_post<LINEAR, NV>(a.red, v[e]);
@@ -1494,28 +1500,29 @@ static bool make_pred_tensor_map(const float* base, int b, int K, int Th, int Tw
 
 constexpr int kMaxTmaBatches = 192;  // 192 x 128 B of tensor maps = 24 KB of kernel parameters (limit 32 KB)
 
-template <int TTA, bool LINEAR, int MAXB, bool DEEP>
+template <int TTA, bool LINEAR, int MAXB, int NG>
 static cudaError_t launch_merge_all_tma_impl2(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
-  const size_t smem = tma_smem_bytes(NV, DEEP);
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = tma_smem_bytes(NV, true);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP>, kTmaThreads, smem);
-    if (e != cudaSuccess) return e;
-    ctas_per_sm = n > 0 ? n : 1;
+    configured = true;
   }
-  const int grid = std::min(nblocks, sm_count() * ctas_per_sm);  // persistent: one resident wave
-  merge_all_tma_kernel<TTA, LINEAR, MAXB, DEEP><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
+  const int grid = std::min((nblocks + NG - 1) / NG, sm_count());  // persistent: one CTA per SM
+  merge_all_tma_kernel<TTA, LINEAR, MAXB, NG><<<grid, kTmaThreads * NG, smem, s>>>(a, maps, nblocks);
   return cudaGetLastError();
 }
 
 template <int TTA, bool LINEAR, int MAXB>
 static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
-  // always the deep ring (1 CTA/SM, ~200 KB of stages): measured 2.17 ms vs 2.30 ms for 2 CTAs x 3 stages on cfg2
-  return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, true>(a, maps, nblocks, s);
+  // D4 (8 views, 32 KB per tile and channel): one pipeline with the deepest ring. Fewer views: two pipelines per CTA.
+  // TB200_MERGE_VARIANT bit0 flips the choice (A/B switch).
+  constexpr int NV = Views<TTA>::count;
+  const bool two = (NV < 8) != ((merge_variant() & 1) != 0);
+  if (two) return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, 2>(a, maps, nblocks, s);
+  return launch_merge_all_tma_impl2<TTA, LINEAR, MAXB, 1>(a, maps, nblocks, s);
 }
 
 template <int TTA, int MAXB>
