@@ -1926,9 +1926,7 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
   // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
-  const bool tiny_stages = (a.views.count * K) < 4;  // 1-2 boxes per block: barrier round trips dominate, plain loads win
-  if (al && pred && !grid->tile_slot && !tiny_stages &&
-      tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
+  if (al && pred && !grid->tile_slot && tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
     TmaMaps<1> maps;
     if (make_pred_tensor_map(pred, grid->n_slots, K, grid->Th, grid->Tw, a.views.count, &maps.m[0])) {
       a.first_tile = 0;

@@ -19,5 +19,8 @@ print("slice_plain ms", round(timed(lambda: eng.slice(image, out=aug)), 3))
 out = torch.empty((1, H, W), dtype=torch.float32, device=dev)
 ref = eng.merge(aug, out=out).clone()
 print("merge tma ms", round(timed(lambda: eng.merge(aug, out=out)), 3), "roundtrip", bool(torch.allclose(out, image.permute(2,0,1).float(), atol=1e-3)))
+os.environ["TB200_MERGE_VARIANT"] = "4"
+print("merge tma forced ms", round(timed(lambda: eng.merge(aug, out=out)), 3), "same bits", bool(torch.equal(out, ref)))
+os.environ["TB200_MERGE_VARIANT"] = "0"
 os.environ["TB200_FORCE_GENERIC_MERGE"] = "1"
 print("merge generic ms", round(timed(lambda: eng.merge(aug, out=out)), 3), "same bits", bool(torch.equal(out, ref)))
