@@ -15,7 +15,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["partition_tile_rows", "StripPlan", "exchange_halo", "sharded_merge"]
+__all__ = ["partition_tile_rows", "StripPlan", "exchange_halo", "sharded_merge", "StripMerger"]
 
 
 def partition_tile_rows(ny: int, world: int) -> List[Tuple[int, int]]:
@@ -123,3 +123,53 @@ def sharded_merge(band_merge: Callable, plan: StripPlan, k: int, wp: int, device
     if interior is not None:
         pieces.append((y_mid, plan.y1, interior))
     return pieces
+
+
+class StripMerger:
+    """``sharded_merge`` for a steady-state loop: buffers, P2P descriptors and launches prepared once, re-run per image.
+
+    ``make_band(rows=(y0,y1), raw=False, init=None)`` returns a prepared band merge -- an object whose ``run()`` merges
+    THIS RANK'S tiles into canvas rows [y0,y1) and returns the band (or the un-normalised ``(num, den)`` pair when
+    raw=True), reading ``init`` (the receive buffers, refilled every step) at run time. On GPUs it is
+    ``TiledInferenceEngine.merge_plan`` bound to the rank's prediction buffers. One ``run()`` then costs three
+    ctypes calls and one ``batch_isend_irecv``; the arithmetic and its order are those of ``sharded_merge``.
+    """
+
+    def __init__(self, make_band: Callable, plan: StripPlan, k: int, wp: int, device, group=None):
+        self.plan, self.group = plan, group
+        self.spill = self.interior = self.top = None
+        self.ops = []
+        self.pieces: List[Tuple[int, int, object]] = []
+        if plan.empty:
+            return
+        if plan.next is not None and plan.halo > 0:
+            self.spill = make_band(rows=(plan.y1, plan.y1 + plan.halo), raw=True, init=None)
+        top_rows = min(plan.halo_in, plan.y1 - plan.y0) if (plan.prev is not None and plan.halo_in > 0) else 0
+        self.y_mid = plan.y0 + top_rows
+        if top_rows:
+            self.recv = (torch.empty((k, top_rows, wp), dtype=torch.float32, device=device),
+                         torch.empty((top_rows, wp), dtype=torch.float32, device=device))
+            self.top = make_band(rows=(plan.y0, self.y_mid), raw=False, init=self.recv)
+        if plan.y1 > self.y_mid:
+            self.interior = make_band(rows=(self.y_mid, plan.y1), raw=False, init=None)
+
+    def run(self):
+        plan = self.plan
+        if plan.empty:
+            return []
+        ops = []
+        if self.top is not None:
+            ops += [dist.P2POp(dist.irecv, self.recv[0], plan.prev, self.group),
+                    dist.P2POp(dist.irecv, self.recv[1], plan.prev, self.group)]
+        if self.spill is not None:
+            num, den = self.spill.run()  # small; first, so it can fly while the interior is merged
+            ops += [dist.P2POp(dist.isend, num, plan.next, self.group), dist.P2POp(dist.isend, den, plan.next, self.group)]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        pieces = []
+        interior = self.interior.run() if self.interior is not None else None
+        wait_all(reqs)
+        if self.top is not None:
+            pieces.append((plan.y0, self.y_mid, self.top.run()))
+        if interior is not None:
+            pieces.append((self.y_mid, plan.y1, interior))
+        return pieces

@@ -25,7 +25,7 @@ from .. import _native as N
 from .._native import TB
 from .tiles import BORDER_CONSTANT, ImageSlicer
 
-__all__ = ["TiledInferenceEngine", "tta_code"]
+__all__ = ["TiledInferenceEngine", "PreparedLaunch", "tta_code"]
 
 _TTA_NAMES = {
     None: TB.TTA_NONE,
@@ -46,6 +46,37 @@ def tta_code(tta) -> int:
     if tta not in _TTA_NAMES:
         raise ValueError(f"Unknown TTA group {tta!r}; expected one of {sorted(k for k in _TTA_NAMES if k)}")
     return _TTA_NAMES[tta]
+
+
+class PreparedLaunch:
+    """One kernel launch with all arguments already marshalled (ctypes structs, pointer arrays, tensor maps inputs).
+
+    ``run()`` costs a single ctypes call: use it for loops that launch the same slice / merge on the same buffers
+    many times (benchmarks, the multi-GPU strip merger, steady-state serving). The launch goes to the CUDA stream that
+    was current when the plan was built and reads / writes the tensors it was built with.
+    """
+
+    __slots__ = ("fn", "args", "keep", "result", "device", "what", "fallback")
+
+    def __init__(self, fn, args, keep, result, device, what, fallback=None):
+        self.fn, self.args, self.keep, self.result, self.device, self.what = fn, args, keep, result, device, what
+        self.fallback = fallback  # () -> (fn, args, what): taken once if the first choice answers TB_ERR_UNSUPPORTED
+
+    def _call(self):
+        if torch.cuda.current_device() == self.device.index:
+            return self.fn(*self.args)
+        with torch.cuda.device(self.device):
+            return self.fn(*self.args)
+
+    def run(self):
+        rc = self._call()
+        if rc == -2 and self.fallback is not None:  # TB_ERR_UNSUPPORTED (nothing was launched): switch kernels for good
+            self.fn, self.args, self.what = self.fallback()
+            self.fallback = None
+            rc = self._call()
+        if rc != 0:
+            N.check(rc, self.what)
+        return self.result
 
 
 class TiledInferenceEngine:
@@ -116,9 +147,9 @@ class TiledInferenceEngine:
         return image.contiguous()
 
     # ------------------------------------------------------------------ slice (+augment)
-    def slice(self, image: torch.Tensor, start: int = 0, stop: Optional[int] = None, layout: str = "HWC",
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Tiles [start, stop) of the grid as the model input batch: float32 [A*n, C, Th, Tw], aug-major."""
+    def slice_plan(self, image: torch.Tensor, start: int = 0, stop: Optional[int] = None, layout: str = "HWC",
+                   out: Optional[torch.Tensor] = None) -> PreparedLaunch:
+        """Prepared launch of ``slice`` (see PreparedLaunch)."""
         stop = self.num_tiles if stop is None else stop
         n = stop - start
         if not (0 <= start <= stop <= self.num_tiles):
@@ -146,17 +177,19 @@ class TiledInferenceEngine:
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous float32 tensor of shape {shape}")
         if n == 0:
-            return out
+            return PreparedLaunch(lambda: 0, (), [], out, image.device, "tb_slice_augment")
         xy = self._bbox_xy[start:stop]
-        with torch.cuda.device(image.device):
-            rc = N.lib().tb_slice_augment(
-                image.data_ptr(), TB.TORCH_DTYPE[image.dtype], layout_code, h, w, c, xy.data_ptr(), n, th, tw, self.tta,
-                self.border_type, self._border_value, N.float_array(self._scale, c) if self._scale is not None else None,
-                N.float_array(self._bias, c) if self._bias is not None else None, out.data_ptr(),
-                N.stream_ptr(image.device),
-            )
-        N.check(rc, "tb_slice_augment")
-        return out
+        scale = N.float_array(self._scale, c) if self._scale is not None else None
+        bias = N.float_array(self._bias, c) if self._bias is not None else None
+        args = (image.data_ptr(), TB.TORCH_DTYPE[image.dtype], layout_code, h, w, c, xy.data_ptr(), n, th, tw, self.tta,
+                self.border_type, self._border_value, scale, bias, out.data_ptr(), N.stream_ptr(image.device))
+        return PreparedLaunch(N.lib().tb_slice_augment, args, [image, xy, out, scale, bias], out, image.device,
+                              "tb_slice_augment")
+
+    def slice(self, image: torch.Tensor, start: int = 0, stop: Optional[int] = None, layout: str = "HWC",
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Tiles [start, stop) of the grid as the model input batch: float32 [A*n, C, Th, Tw], aug-major."""
+        return self.slice_plan(image, start, stop, layout, out).run()
 
     # ------------------------------------------------------------------ merge
     def _grid(self, n_slots: int) -> N.Grid:
@@ -172,7 +205,23 @@ class TiledInferenceEngine:
         raw: bool = False,
         init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
     ):
-        """All predictions -> merged, normalised, cropped logits float32 [K,H,W].
+        """All predictions -> merged, normalised, cropped logits float32 [K,H,W] (see ``merge_plan`` for the arguments)."""
+        plan = self.merge_plan(preds, out, rows, tile_rows, raw, init)
+        result = plan.run()
+        # tables / casts must outlive the asynchronous launch: park them until the next call on this engine
+        self._keepalive = plan.keep
+        return result
+
+    def merge_plan(
+        self,
+        preds: Union[torch.Tensor, Sequence[torch.Tensor]],
+        out: Optional[torch.Tensor] = None,
+        rows: Optional[Tuple[int, int]] = None,
+        tile_rows: Optional[Tuple[int, int]] = None,
+        raw: bool = False,
+        init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+    ) -> PreparedLaunch:
+        """Prepared launch: all predictions -> merged, normalised, cropped logits float32 [K,H,W].
 
         ``preds`` is either one tensor [A*N,K,Th,Tw] (aug-major over the whole grid) or the list of the model's
         per-batch outputs ([A*b,K,Th,Tw] each, batches in grid order) -- the latter is merged in place (one TMA
@@ -216,10 +265,8 @@ class TiledInferenceEngine:
         uniform = all(sz == sizes[0] for sz in sizes[:-1]) and sizes[-1] <= sizes[0]
         whole_grid_single = len(batches) == 1 and sizes[0] == self.num_tiles
         mode = "single" if whole_grid_single else ("batched" if uniform else "table")
-        pred_ptr = None
-        if mode == "single":
-            pred_ptr = batches[0].data_ptr()
-        elif mode == "table":
+
+        def pointer_table():
             ptrs = np.zeros(self.num_tiles, dtype=np.int64)
             vstr = np.zeros(self.num_tiles, dtype=np.int64)
             t = first_tile
@@ -229,9 +276,13 @@ class TiledInferenceEngine:
                 t += b
             ptr_dev = torch.from_numpy(ptrs).to(device)
             vstr_dev = torch.from_numpy(vstr).to(device)
-            keep += [ptr_dev, vstr_dev]
+            keep.extend([ptr_dev, vstr_dev])
             grid.tile_ptr = ptr_dev.data_ptr()
             grid.tile_vstride = vstr_dev.data_ptr()
+
+        pred_ptr = batches[0].data_ptr() if mode == "single" else None
+        if mode == "table":
+            pointer_table()
         top, left = self.slicer.margin_top, self.slicer.margin_left
         h, w = self.slicer.image_height, self.slicer.image_width
         init_num = init_den = None
@@ -240,6 +291,7 @@ class TiledInferenceEngine:
             if tuple(init_num.shape) != (k, y1 - y0, wp) or tuple(init_den.shape) != (y1 - y0, wp):
                 raise ValueError("init must be (num [K,rows,Wp], den [rows,Wp])")
             init_num, init_den = init_num.contiguous(), init_den.contiguous()
+            keep.extend([init_num, init_den])
         if raw:
             num = torch.empty((k, y1 - y0, wp), dtype=torch.float32, device=device)
             den = torch.empty((y1 - y0, wp), dtype=torch.float32, device=device)
@@ -250,33 +302,22 @@ class TiledInferenceEngine:
             elif tuple(out.shape) != (k, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous float32 tensor [{k},{h},{w}]")
             out_num, out_den, result = out.data_ptr(), None, out
+        grid_ref = C.byref(grid)
         common = (k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1, N.ptr(init_num), N.ptr(init_den),
                   1 if raw else 0, top, left, h, w, out_num, out_den, N.stream_ptr(device))
-        with torch.cuda.device(device):
-            rc = None
-            if mode == "batched":
-                ptr_arr = (C.c_void_p * len(batches))(*[b.data_ptr() for b in batches])
-                rc = N.lib().tb_merge_all_batched(ptr_arr, len(batches), sizes[0], sizes[-1], first_tile, C.byref(grid), *common)
-                if rc == -2:  # TB_ERR_UNSUPPORTED: geometry off the TMA lattice -> pointer-table kernel
-                    rc = None
-                    ptrs = np.zeros(self.num_tiles, dtype=np.int64)
-                    vstr = np.zeros(self.num_tiles, dtype=np.int64)
-                    t = first_tile
-                    for batch, b in zip(batches, sizes):
-                        ptrs[t : t + b] = batch.data_ptr() + np.arange(b, dtype=np.int64) * (plane_set * 4)
-                        vstr[t : t + b] = b * plane_set
-                        t += b
-                    ptr_dev = torch.from_numpy(ptrs).to(device)
-                    vstr_dev = torch.from_numpy(vstr).to(device)
-                    keep += [ptr_dev, vstr_dev]
-                    grid.tile_ptr = ptr_dev.data_ptr()
-                    grid.tile_vstride = vstr_dev.data_ptr()
-            if rc is None:
-                rc = N.lib().tb_merge_all(pred_ptr, C.byref(grid), *common)
-        N.check(rc, "tb_merge_all")
-        # tables must outlive the asynchronous launch: park them until the next call on this engine
-        self._keepalive = keep
-        return result
+        keep += [grid, self._weight, self._weight_table, result]
+        if mode == "batched":
+            ptr_arr = (C.c_void_p * len(batches))(*[b.data_ptr() for b in batches])
+            keep.append(ptr_arr)
+            args = (ptr_arr, len(batches), sizes[0], sizes[-1], first_tile, grid_ref) + common
+
+            def to_table():  # geometry off the TMA lattice -> pointer-table kernel
+                pointer_table()
+                return N.lib().tb_merge_all, (None, grid_ref) + common, "tb_merge_all"
+
+            return PreparedLaunch(N.lib().tb_merge_all_batched, args, keep, result, device, "tb_merge_all_batched", to_table)
+        args = (pred_ptr, grid_ref) + common
+        return PreparedLaunch(N.lib().tb_merge_all, args, keep, result, device, "tb_merge_all")
 
     # ------------------------------------------------------------------ whole pipeline
     @torch.no_grad()

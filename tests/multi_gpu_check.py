@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pytorch_toolbelt_b200.distributed.strips import StripPlan, sharded_merge  # noqa: E402
+from pytorch_toolbelt_b200.distributed.strips import StripMerger, StripPlan, sharded_merge  # noqa: E402
 from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine  # noqa: E402
 
 
@@ -46,6 +46,21 @@ def main():
             same = torch.equal(out[:, a:b], reference[:, a:b])
             ok = ok and same
             print(f"rank {rank}/{world} {shape} T{T}/S{S} {tta}: rows [{a},{b}) bit-exact={same}", flush=True)
+
+        # steady-state form (prepared launches, persistent halo buffers): same rows, step after step
+        def band_plan(rows, raw=False, init=None):
+            return eng.merge_plan(own, out=None if raw else out, rows=rows, tile_rows=(plan.r0, plan.r1), raw=raw, init=init)
+
+        merger = StripMerger(band_plan, plan, K, wp, dev)
+        for it in range(3):
+            out.fill_(float("nan"))
+            merger.run()
+            torch.cuda.synchronize()
+            if not plan.empty and b > a:
+                same = torch.equal(out[:, a:b], reference[:, a:b])
+                ok = ok and same
+                if not same:
+                    print(f"rank {rank}/{world} {shape}: StripMerger step {it} MISMATCH", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import tiles_oracle as TO
-from pytorch_toolbelt_b200.distributed.strips import StripPlan, partition_tile_rows, sharded_merge
+from pytorch_toolbelt_b200.distributed.strips import StripMerger, StripPlan, partition_tile_rows, sharded_merge
 
 
 def test_partition_tile_rows():
@@ -75,6 +75,22 @@ def _worker(rank, world, port, shape, tile, step, K, result_dir):
         band = _band_merger(grid, weight, preds, K, (plan.r0, plan.r1), nx)
         pieces = sharded_merge(band, plan, K, wp, torch.device("cpu"))
         torch.save([(a, b, t) for a, b, t in pieces], os.path.join(result_dir, f"rank{rank}.pt"))
+        dist.barrier()
+
+        # the prepared (steady-state) form must give the same pieces, step after step, from the same buffers
+        class _Band:
+            def __init__(self, rows, raw=False, init=None):
+                self.rows, self.raw, self.init = rows, raw, init
+
+            def run(self):
+                return band(self.rows, raw=self.raw, init=self.init)
+
+        merger = StripMerger(_Band, plan, K, wp, torch.device("cpu"))
+        for _ in range(2):
+            again = merger.run()
+            assert len(again) == len(pieces)
+            for (a0, b0, t0), (a1, b1, t1) in zip(pieces, again):
+                assert (a0, b0) == (a1, b1) and torch.equal(t0, t1)
         dist.barrier()
     finally:
         dist.destroy_process_group()

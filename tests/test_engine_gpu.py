@@ -156,6 +156,63 @@ def test_band_mode_reproduces_full_merge():
     assert torch.equal(rows_of(rest, y_split + 64, hp), rows_of(full, y_split + 64, hp))
 
 
+@pytest.mark.gpu
+def test_prepared_plans_rerun_on_refilled_buffers():
+    """slice_plan / merge_plan (the steady-state form used by the multi-GPU loop): marshalled once, run() re-launches on
+    whatever the bound buffers hold now. Three strips are emulated on one GPU; each strip's predictions are its own
+    tensor (only its tiles resident), the halo buffers are refilled every step."""
+    from pytorch_toolbelt_b200.distributed.strips import StripPlan
+
+    rng = np.random.default_rng(5)
+    image_shape = (900, 500, 3)
+    K, T, S = 2, 128, 64
+    eng = TiledInferenceEngine(image_shape, T, S, channels=K, weight="pyramid", tta="fliplr")
+    ny, nx = eng.slicer.grid_shape
+    hp, wp = eng.slicer.target_shape
+    world = 3
+    plans = [StripPlan.build(ny, T, S, hp, g, world) for g in range(world)]
+    image = eng.to_device(rng.integers(0, 256, image_shape).astype(np.uint8))
+    A = eng.views
+    strips = []
+    out = torch.zeros((K, image_shape[0], image_shape[1]), device="cuda")
+    for p in plans:
+        n_own = (p.r1 - p.r0) * nx
+        pred = torch.empty((A * n_own, K, T, T), device="cuda")
+        aug = torch.empty((A * n_own, 3, T, T), device="cuda")
+        band = lambda rows, raw=False, init=None, pred=pred, p=p: eng.merge_plan(  # noqa: E731
+            pred, out=None if raw else out, rows=rows, tile_rows=(p.r0, p.r1), raw=raw, init=init)
+        top_rows = p.halo_in
+        recv = (torch.empty((K, top_rows, wp), device="cuda"), torch.empty((top_rows, wp), device="cuda")) if top_rows else None
+        strips.append(dict(
+            plan=p, pred=pred, aug=aug, recv=recv,
+            slicer=eng.slice_plan(image, p.r0 * nx, p.r1 * nx, out=aug),
+            spill=band((p.y1, p.y1 + p.halo), raw=True) if p.halo else None,
+            top=band((p.y0, p.y0 + top_rows), init=recv) if top_rows else None,
+            interior=band((p.y0 + top_rows, p.y1)),
+        ))
+    for step in range(2):
+        full_pred = torch.randn(A * eng.num_tiles, K, T, T, generator=torch.Generator().manual_seed(step)).cuda()
+        want = eng.merge(full_pred)
+        want_aug = eng.slice(image)
+        out.fill_(float("nan"))
+        by_view = full_pred.view(A, eng.num_tiles, K, T, T)
+        for st in strips:
+            p = st["plan"]
+            st["pred"].view(A, -1, K, T, T).copy_(by_view[:, p.r0 * nx : p.r1 * nx])
+            got_aug = st["slicer"].run()
+            assert got_aug is st["aug"]
+            assert torch.equal(got_aug.view(A, -1, 3, T, T), want_aug.view(A, eng.num_tiles, 3, T, T)[:, p.r0 * nx : p.r1 * nx])
+        for g, st in enumerate(strips):
+            if st["spill"] is not None:
+                num, den = st["spill"].run()
+                strips[g + 1]["recv"][0].copy_(num)
+                strips[g + 1]["recv"][1].copy_(den)
+            if st["top"] is not None:
+                st["top"].run()
+            st["interior"].run()
+        assert torch.equal(out, want), f"step {step}"
+
+
 def test_full_size_properties_cfg2():
     """BASELINE cfg 2 geometry (5000x5000x3, 512/256, d4, K=4) through size-independent properties:
     constant predictions merge to the constant; D4 de-augment of an augmented constant-per-view field is exact;
