@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 from .. import _native as N
 from ..inference.engine import TiledInferenceEngine
+from ..utils.clocks import ClockSampler
 from .strips import StripMerger, StripPlan, partition_tile_rows
 
 
@@ -87,8 +88,20 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(True)
-    ms_step = timed(step, args.steps)
-    ms_with_model = timed(lambda: step(True), args.steps)
+    # clocks of rank 0's GPU during the timed region (every rank runs the same kernels on the same kind of GPU)
+    with ClockSampler(local, uuid=str(getattr(torch.cuda.get_device_properties(dev), "uuid", "")) or None) as clocks:
+        ms_step = timed(step, args.steps)
+        ms_with_model = timed(lambda: step(True), args.steps)
+        extra = 0
+        while extra < 200:  # same load, untimed, until the sampler has 3 readings (all ranks take the same decision)
+            need = torch.tensor([1 if (clocks.samples < 3 and clocks.source != "unavailable") else 0], device=dev)
+            dist.broadcast(need, src=0)
+            if int(need.item()) == 0:
+                break
+            for _ in range(10):
+                step()
+            extra += 10
+    clk = clocks.summary()
 
     # e2e through the public API with host buffers: every rank uploads the image, runs its strip, downloads its rows
     top = eng.slicer.margin_top
@@ -130,6 +143,7 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
                     "h2d_bytes_per_step": H * W * Cin * world, "d2h_bytes_per_step": K * H * W * 4,
                     "api": "per rank: pinned host image -> TiledInferenceEngine.slice/merge on its strip -> pinned host strip"},
             "gpu_launches": (1 + 3) * args.steps,
+            "clocks": clk,
         }
         print(json.dumps(line))
     dist.barrier()
