@@ -1,1 +1,1 @@
-from .strips import StripPlan, exchange_halo, partition_tile_rows, sharded_merge  # noqa: F401
+from .strips import StripMerger, StripPlan, exchange_halo, partition_tile_rows, sharded_merge  # noqa: F401

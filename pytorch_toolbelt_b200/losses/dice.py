@@ -82,6 +82,13 @@ class _RegionLoss(torch.autograd.Function):
             rc = N.lib().tb_dice_stats(x3.data_ptr(), t.data_ptr(), t_kind, b, c, inner, C.byref(p), stats.data_ptr(),
                                        ws.data_ptr(), ws.numel(), stream)
             N.check(rc, "tb_dice_stats")
+            if cfg.get("sync"):
+                # data-parallel over the batch: the per-class sums are the only thing that crosses ranks.
+                # The loss value becomes the global-batch loss on every rank and the gradient kernel below, fed the
+                # global sums, yields d(global loss)/d(local logits) -- no further reduction is needed.
+                import torch.distributed as dist
+
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=cfg.get("group"))
             rc = N.lib().tb_dice_loss_grad(x3.data_ptr(), t.data_ptr(), t_kind, b, c, inner, C.byref(p), stats.data_ptr(),
                                            N.ptr(cls_dev), 0 if cls_dev is None else cls_dev.numel(), out.data_ptr(),
                                            N.ptr(grad), stream)
@@ -143,4 +150,8 @@ class DiceLoss(_Loss):
         assert y_true.size(0) == y_pred.size(0)
         cfg = dict(jaccard=False, mode=self.mode, classes=self.classes, log_loss=self.log_loss,
                    from_logits=self.from_logits, smooth=self.smooth, eps=self.eps, ignore_index=self.ignore_index)
+        cfg.update(self._sync_cfg())
         return _RegionLoss.apply(y_pred, y_true, cfg)
+
+    def _sync_cfg(self) -> dict:
+        return {}

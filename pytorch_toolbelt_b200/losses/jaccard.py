@@ -30,4 +30,8 @@ class JaccardLoss(_Loss):
         assert y_true.size(0) == y_pred.size(0)
         cfg = dict(jaccard=True, mode=self.mode, classes=self.classes, log_loss=self.log_loss,
                    from_logits=self.from_logits, smooth=self.smooth, eps=self.eps, ignore_index=None)
+        cfg.update(self._sync_cfg())
         return _RegionLoss.apply(y_pred, y_true, cfg)
+
+    def _sync_cfg(self) -> dict:
+        return {}

@@ -17,6 +17,45 @@ from pytorch_toolbelt_b200.distributed.strips import StripMerger, StripPlan, sha
 from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine  # noqa: E402
 
 
+def losses_check(rank, world, dev):
+    """Sync{Dice,Jaccard}Loss on a batch shard per rank == the single-GPU loss of the whole batch (value and the
+    gradient rows of the shard); the only cross-rank traffic is the float64 [C,3] all-reduce."""
+    import pytorch_toolbelt_b200.losses as L
+    from pytorch_toolbelt_b200.distributed.losses import SyncDiceLoss, SyncJaccardLoss
+
+    per = 2
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(per * world, 4, 96, 80, generator=g) * 3).to(dev)
+    t_ml = (torch.rand(per * world, 4, 96, 80, generator=g) < 0.3).float().to(dev)
+    t_mc = torch.randint(0, 4, (per * world, 96, 80), generator=g).to(dev)
+    mine = slice(per * rank, per * rank + per)
+    ok = True
+    cases = [
+        ("dice multilabel", L.DiceLoss("multilabel"), SyncDiceLoss("multilabel"), t_ml),
+        ("dice multiclass log smooth", L.DiceLoss("multiclass", log_loss=True, smooth=1.0),
+         SyncDiceLoss("multiclass", log_loss=True, smooth=1.0), t_mc),
+        ("jaccard multilabel", L.JaccardLoss("multilabel", smooth=0.5), SyncJaccardLoss("multilabel", smooth=0.5), t_ml),
+    ]
+    for name, whole_loss, sync_loss, t in cases:
+        xw = x.clone().requires_grad_(True)
+        whole = whole_loss(xw, t)
+        whole.backward()
+        xl = x[mine].clone().requires_grad_(True)
+        synced = sync_loss(xl, t[mine])
+        synced.backward()
+        torch.cuda.synchronize()
+        v_ok = abs(float(synced) - float(whole)) <= 1e-6 * max(1.0, abs(float(whole)))
+        scale = float(xw.grad.abs().max())
+        g_ok = float((xl.grad - xw.grad[mine]).abs().max()) <= 1e-5 * scale + 1e-12
+        if not (v_ok and g_ok):
+            print(f"rank {rank}/{world} {name}: value {float(synced)} vs {float(whole)}, "
+                  f"grad max err {float((xl.grad - xw.grad[mine]).abs().max())} (scale {scale}) MISMATCH", flush=True)
+        ok = ok and v_ok and g_ok
+    if rank == 0:
+        print(f"sync losses over {world} ranks: {'ok' if ok else 'MISMATCH'}", flush=True)
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -61,6 +100,7 @@ def main():
                 ok = ok and same
                 if not same:
                     print(f"rank {rank}/{world} {shape}: StripMerger step {it} MISMATCH", flush=True)
+    ok = losses_check(rank, world, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -113,3 +113,48 @@ def test_sharded_merge_matches_single_process(world, tmp_path):
             assert not covered[y0:y1].any()
             covered[y0:y1] = True
     assert covered.all()
+
+
+def _loss_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import losses_oracle as LO
+        from pytorch_toolbelt_b200.distributed.losses import global_mean
+
+        g = torch.Generator().manual_seed(11)
+        x = torch.randn(4 * world, 3, 16, 16, generator=g) * 3
+        t = (torch.rand(4 * world, 3, 16, 16, generator=g) < 0.3).float()
+        mine = slice(4 * rank, 4 * rank + 4)
+        # (1) what SyncDiceLoss exchanges: the per-class sums over (batch, space) add up over batch shards, and the
+        #     loss of the summed statistics is the loss of the whole batch (multilabel, smooth 0, eps 1e-7)
+        p = torch.sigmoid(x[mine]).double()
+        tt = t[mine].double()
+        stats = torch.stack([(p * tt).sum(dim=(0, 2, 3)), (p + tt).sum(dim=(0, 2, 3)), tt.sum(dim=(0, 2, 3))], dim=1)
+        dist.all_reduce(stats)
+        inter, card, tsum = stats[:, 0], stats[:, 1], stats[:, 2]
+        score = (2.0 * inter) / card.clamp_min(1e-7)
+        synced = ((1.0 - score) * (tsum > 0)).mean()
+        whole = LO.dice_loss(x, t, "multilabel")
+        assert abs(float(synced) - float(whole)) <= 1e-6 * max(1.0, abs(float(whole))), (float(synced), float(whole))
+        # (2) global_mean: value = mean over ranks, gradient = 1/world to the local term
+        xl = x[mine].clone().requires_grad_(True)
+        local = LO.focal_sigmoid(xl, t[mine], alpha=None)
+        glob = global_mean(local)
+        glob.backward()
+        xw = x.clone().requires_grad_(True)
+        whole_focal = LO.focal_sigmoid(xw, t, alpha=None)
+        whole_focal.backward()
+        torch.testing.assert_close(glob.detach(), whole_focal.detach(), rtol=1e-6, atol=1e-9)
+        torch.testing.assert_close(xl.grad, xw.grad[mine], rtol=1e-5, atol=1e-10)
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_loss_reductions(tmp_path):
+    world = 2
+    mp.spawn(_loss_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
