@@ -298,6 +298,17 @@ TB_API int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t 
                       const tb_dice_params* p, const double* stats /*[C,3]*/, const int32_t* classes /*NULL or [n_classes]*/,
                       int n_classes, float* loss_out, float* grad, void* stream);
 
+/* Joint sigmoid focal + dice / jaccard on a dense f32 target [B,C,inner] (BASELINE config 3:
+ * BinaryFocalLoss + DiceLoss summed by the caller, focal.py:13-105 + dice.py:18-131): loss = w_focal * focal +
+ * w_dice * region, and its gradient, in two passes over (x, t) and one gradient write.
+ * Restrictions (TB_ERR_UNSUPPORTED otherwise): focal sigmoid, not normalised, reduction MEAN or SUM; region mode
+ * binary / multilabel with from_logits. loss_out f32 [3] = (total, focal term, region term), unweighted terms.
+ * EXPERIMENTAL in round 1: compiled and exported, not yet validated on a GPU (tests are opt-in, TB200_EXPERIMENTAL=1). */
+TB_API int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int64_t inner, const tb_focal_params* fp,
+                          const float* class_w, const tb_dice_params* dp, const int32_t* classes, int n_classes,
+                          float w_focal, float w_dice, float* loss_out, float* grad, void* ws, size_t ws_bytes,
+                          void* stream);
+
 /* Wing loss. Replaces wing_loss (losses/functional.py:250-277). reduction NONE/MEAN/SUM.
  * grad = d loss / d x (NULL to skip); target gets no gradient here (shim negates for it). */
 TB_API int tb_wing_fwd_bwd(const float* x, const float* t, int64_t n, float width, float curvature, int reduction,

@@ -146,6 +146,10 @@ SIGNATURES = {
     ),
     "tb_dice_stats": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(DiceParams), _vp, _vp, _sz, _vp]),
     "tb_dice_loss_grad": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(DiceParams), _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb_focal_dice_fwd_bwd": (
+        _i,
+        [_vp, _vp, _i64, _i, _i64, C.POINTER(FocalParams), _vp, C.POINTER(DiceParams), _vp, _i, _f, _f, _vp, _vp, _vp, _sz, _vp],
+    ),
     "tb_wing_fwd_bwd": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "tb_scale_by_device_scalar": (_i, [_vp, _i64, _vp, _vp]),
     "tb_lovasz_sorted": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),

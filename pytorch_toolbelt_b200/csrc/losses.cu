@@ -780,6 +780,153 @@ __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
 }
 
 // =================================================================================================
+// joint sigmoid-focal + dice / jaccard on a dense target (BASELINE config 3: BinaryFocalLoss + DiceLoss)
+// Two passes over (x, t) and ONE gradient write: 2*(N+N)*4 + N*4 bytes instead of the 3N*4 (focal) + 5N*4
+// (dice) + 3N*4 (adding the two gradients) of the separate kernels. One exp per element per pass serves the
+// sigmoid, the softplus of the BCE term and the dice probability.
+// =================================================================================================
+struct JointArgs {
+  const float* x;
+  const float* t;
+  long long B, inner;
+  int C;
+  FocalDev f;        // sigmoid activation, not normalised, reduction MEAN or SUM
+  tb_dice_params d;  // mode 0 / 2, from_logits
+  const int* classes;
+  int n_classes;
+  float w_focal, w_dice;
+  float gscale;      // focal: 1/numel for MEAN, 1 for SUM
+  double* partials;  // pass 1: [rows][chunks][4] = (I, S, T, focal sum)
+  double* stats;     // [C][4], written by the finalize kernel, read by pass 2
+  float* grad;
+  float* loss_out;   // [3]: total, focal, dice
+  int chunks;
+};
+
+// shared by both passes so that they see identical p / loss terms
+__device__ __forceinline__ void joint_elem(const JointArgs& a, float x, float t, int c, float& pr, float& L, float& dL) {
+  const float ex = __expf(-fabsf(x));
+  const float inv = 1.f / (1.f + ex);
+  pr = x >= 0.f ? inv : ex * inv;
+  float F, dF;
+  focal_elem(a.f, x, t, pr, pr * (1.f - pr), pr, softplus_from_exp(ex), c, L, F, dL, dF);
+}
+
+template <int VW>
+__global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
+  const long long row = blockIdx.y;  // b*C + c
+  const int c = (int)(row % a.C);
+  const long long innerv = a.inner / VW;
+  const float* xr = a.x + row * a.inner;
+  const float* tr = a.t + row * a.inner;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < innerv; v += (long long)gridDim.x * kLT) {
+    float xs[VW], ts[VW];
+    ld_vec<VW>(xr, v, xs);
+    ld_vec<VW>(tr, v, ts);
+    float I = 0.f, S = 0.f, T = 0.f, Ls = 0.f;
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      float pr, L, dL;
+      joint_elem(a, xs[e], ts[e], c, pr, L, dL);
+      Ls += L;
+      float t = ts[e];
+      if (a.d.has_ignore && t == a.d.ignore_index) {  // dice.py:85-88,107-111
+        pr = 0.f;
+        t = 0.f;
+      }
+      I += pr * t;
+      S += pr + t;
+      T += t;
+    }
+    acc[0] += (double)I;
+    acc[1] += (double)S;
+    acc[2] += (double)T;
+    acc[3] += (double)Ls;
+  }
+  block_reduce<4>(acc);
+  if (threadIdx.x == 0) {
+    double* o = a.partials + ((size_t)row * gridDim.x + blockIdx.x) * 4;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+  }
+}
+
+// stats[c] = sum over b and chunks in a fixed order (deterministic)
+__global__ void __launch_bounds__(kLT) joint_finalize_kernel(const double* partials, long long B, int C, int chunks,
+                                                             double* stats) {
+  const int c = blockIdx.x;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  const long long count = B * chunks;
+  for (long long i = threadIdx.x; i < count; i += kLT) {
+    const long long b = i / chunks, ch = i - b * chunks;
+    const double* p = partials + ((size_t)(b * C + c) * chunks + ch) * 4;
+    v[0] += p[0]; v[1] += p[1]; v[2] += p[2]; v[3] += p[3];
+  }
+  block_reduce<4>(v);
+  if (threadIdx.x == 0) {
+    stats[4 * c] = v[0]; stats[4 * c + 1] = v[1]; stats[4 * c + 2] = v[2]; stats[4 * c + 3] = v[3];
+  }
+}
+
+template <int VW>
+__global__ void __launch_bounds__(kLT) joint_grad_kernel(JointArgs a) {
+  extern __shared__ float sh_coef[];  // [C][2]: w_dice * (alpha, beta) / number of averaged classes
+  const int nsel = a.classes ? a.n_classes : a.C;
+  for (int c = threadIdx.x; c < a.C; c += kLT) {
+    double lc;
+    float al, be;
+    region_class_terms(a.d, a.stats + 4 * c, lc, al, be);
+    int mult = 1;
+    if (a.classes) {
+      mult = 0;
+      for (int k = 0; k < a.n_classes; ++k) mult += (a.classes[k] == c);
+    }
+    sh_coef[2 * c] = a.w_dice * al * (float)mult / (float)nsel;
+    sh_coef[2 * c + 1] = a.w_dice * be * (float)mult / (float)nsel;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_out) {  // serial, fixed order: deterministic
+    double dice = 0.0, focal = 0.0;
+    for (int c = 0; c < a.C; ++c) {
+      double lc;
+      float al, be;
+      region_class_terms(a.d, a.stats + 4 * c, lc, al, be);
+      int mult = 1;
+      if (a.classes) {
+        mult = 0;
+        for (int k = 0; k < a.n_classes; ++k) mult += (a.classes[k] == c);
+      }
+      dice += lc * mult / nsel;
+      focal += a.stats[4 * c + 3];
+    }
+    focal *= (double)a.gscale;
+    a.loss_out[0] = (float)((double)a.w_focal * focal + (double)a.w_dice * dice);
+    a.loss_out[1] = (float)focal;
+    a.loss_out[2] = (float)dice;
+  }
+  __syncthreads();
+  if (!a.grad) return;
+  const long long totalv = a.B * a.C * a.inner / VW, innerv = a.inner / VW;
+  const float fscale = a.w_focal * a.gscale;
+  for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < totalv; v += (long long)gridDim.x * kLT) {
+    const int c = (int)((v / innerv) % a.C);
+    const float al = sh_coef[2 * c], be = sh_coef[2 * c + 1];
+    float xs[VW], ts[VW], g[VW];
+    ld_vec<VW>(a.x, v, xs);
+    ld_vec<VW>(a.t, v, ts);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      float pr, L, dL;
+      joint_elem(a, xs[e], ts[e], c, pr, L, dL);
+      const float t = ts[e];
+      const bool ign = a.d.has_ignore && t == a.d.ignore_index;
+      const float gd = ign ? 0.f : (al * t + be) * (pr * (1.f - pr));
+      g[e] = fscale * dL + gd;
+    }
+    st_vec<VW>(a.grad, v, g);
+  }
+}
+
+// =================================================================================================
 // wing
 // =================================================================================================
 struct WingArgs {
@@ -972,6 +1119,7 @@ size_t tb_loss_workspace_bytes(int64_t B, int C, int64_t inner) {
   bytes = std::max(bytes, (grid * 2 + 8) * sizeof(double));
   bytes = std::max(bytes, ((size_t)B * C * chunks * 3 + 8) * sizeof(double));
   bytes = std::max(bytes, (grid * (size_t)C * 3 + 8) * sizeof(double));
+  bytes = std::max(bytes, ((size_t)B * C * chunks * 4 + (size_t)C * 4 + 8) * sizeof(double));  // joint focal + dice
   (void)inner;
   return align_up(bytes, 256) + 256;
 }
@@ -1192,6 +1340,48 @@ int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t B, int 
   else
     region_grad_kernel<1><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
   TB_LAUNCH_CHECK("region_grad_kernel");
+  return TB_OK;
+}
+
+int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int64_t inner, const tb_focal_params* fp,
+                          const float* class_w, const tb_dice_params* dp, const int32_t* classes, int n_classes,
+                          float w_focal, float w_dice, float* loss_out, float* grad, void* ws, size_t ws_bytes,
+                          void* stream) {
+  TB_REQUIRE(x && t && fp && dp && loss_out && ws, TB_ERR_ARG, "tb_focal_dice_fwd_bwd: null pointer");
+  TB_REQUIRE(B > 0 && C > 0 && inner > 0, TB_ERR_ARG, "tb_focal_dice_fwd_bwd: bad shape");
+  TB_REQUIRE(!fp->softmax && !fp->normalized && (fp->reduction == TB_LOSS_MEAN || fp->reduction == TB_LOSS_SUM),
+             TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: focal term must be sigmoid, not normalised, mean or sum reduced");
+  TB_REQUIRE((dp->mode == 0 || dp->mode == 2) && dp->from_logits, TB_ERR_UNSUPPORTED,
+             "tb_focal_dice_fwd_bwd: region term must be binary / multilabel on logits");
+  TB_REQUIRE(B * C <= 65535 && C <= 4096, TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: B*C must be <= 65535, C <= 4096");
+  TB_REQUIRE(!classes || n_classes > 0, TB_ERR_ARG, "tb_focal_dice_fwd_bwd: empty class list");
+  TB_REQUIRE(ws_bytes >= tb_loss_workspace_bytes(B, C, inner), TB_ERR_WORKSPACE, "tb_focal_dice_fwd_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  JointArgs a{};
+  a.x = x; a.t = t; a.B = B; a.inner = inner; a.C = C;
+  a.f.p = *fp; a.f.cw = class_w; a.d = *dp; a.classes = classes; a.n_classes = n_classes;
+  a.w_focal = w_focal; a.w_dice = w_dice;
+  a.gscale = fp->reduction == TB_LOSS_MEAN ? (float)(1.0 / ((double)B * C * inner)) : 1.f;
+  a.grad = grad; a.loss_out = loss_out;
+  const bool vec4 = (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 &&
+                    (!grad || (reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+  const long long innerv = inner / (vec4 ? 4 : 1);
+  const int chunks = (int)std::max<long long>(1, std::min<long long>(64, (innerv + kLT * 4 - 1) / (kLT * 4)));
+  a.chunks = chunks;
+  a.partials = static_cast<double*>(ws);
+  a.stats = a.partials + (size_t)B * C * chunks * 4;
+  dim3 grid1(chunks, (unsigned)(B * C));
+  if (vec4)
+    joint_stats_kernel<4><<<grid1, kLT, 0, s>>>(a);
+  else
+    joint_stats_kernel<1><<<grid1, kLT, 0, s>>>(a);
+  joint_finalize_kernel<<<C, kLT, 0, s>>>(a.partials, B, C, chunks, a.stats);
+  const int grid2 = grad ? loss_grid(B * C * inner / (vec4 ? 4 : 1)) : 1;
+  if (vec4)
+    joint_grad_kernel<4><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
+  else
+    joint_grad_kernel<1><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
+  TB_LAUNCH_CHECK("joint_focal_dice_kernel");
   return TB_OK;
 }
 

@@ -5,5 +5,6 @@ from .dice import *  # noqa: F401,F403
 from .focal import *  # noqa: F401,F403
 from .functional import *  # noqa: F401,F403
 from .jaccard import *  # noqa: F401,F403
+from .joint import *  # noqa: F401,F403
 from .lovasz import *  # noqa: F401,F403
 from .wing_loss import *  # noqa: F401,F403
