@@ -161,7 +161,6 @@ struct FocalArgs {
   // second pass of the normalised loss: grad = gs * (dL/N - sumL/N^2 * dF)
   const double* sums;  // [2] (sum L, sum F) or null
   float gscale;        // 1/numel for mean, 1 for sum / none
-  int elem_scaled_by_norm;  // NONE/BATCHWISE + normalized: loss_elem = L / N
 };
 
 // PASS: 0 = single pass (not normalised): partial sums + loss_elem + grad
@@ -442,10 +441,6 @@ struct RegionArgs {
   float* loss_out;
   int chunks;             // CTAs per (b,c) row in the elementwise stats pass
 };
-
-__device__ __forceinline__ float region_target(const RegionArgs& a, const void* t, long long idx) {
-  return __ldcs(static_cast<const float*>(t) + idx);
-}
 
 // binary / multilabel: rows are (b,c) pairs of `inner` contiguous elements
 template <int VW>
@@ -1152,7 +1147,6 @@ int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C
   double* partials = static_cast<double*>(ws);
   const bool elem_out = p->reduction == TB_LOSS_NONE;
   const bool batchwise = p->reduction == TB_LOSS_BATCHWISE;
-  TB_REQUIRE(!(batchwise && !grad && false), TB_ERR_ARG, "unreachable");
   const float gscale = p->reduction == TB_LOSS_MEAN ? (float)(1.0 / numel) : 1.f;
 
   if (p->softmax) {
@@ -1187,17 +1181,13 @@ int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C
   FocalArgs a;
   a.x = x; a.t = t; a.t_kind = t_kind; a.B = B; a.inner = inner; a.C = C;
   a.f.p = *p; a.f.cw = class_w;
-  a.grad = grad; a.gscale = gscale; a.sums = nullptr; a.elem_scaled_by_norm = 0;
+  a.grad = grad; a.gscale = gscale; a.sums = nullptr;
   const int grid = loss_grid(B * C * inner / (vec4 ? 4 : 1));
   a.partials = partials;
   double* sums = partials + 2 * (size_t)grid;
   float* elem_buf = nullptr;
   if (elem_out) elem_buf = loss_out;
-  if (batchwise) {
-    // element losses go to the gradient-shaped scratch the caller provides through `grad`? No: batchwise needs its
-    // own [B,C,inner] scratch; the shim passes it as loss_out + C*inner (documented in tb200.h).
-    elem_buf = loss_out + (size_t)C * inner;
-  }
+  if (batchwise) elem_buf = loss_out + (size_t)C * inner;  // scratch for the element losses behind the result (tb200.h)
   a.loss_elem = elem_buf;
   const bool labels = t_kind == TB_T_LABELS_I64;
 #define TB_FOCAL_LAUNCH(PASS)                                            \

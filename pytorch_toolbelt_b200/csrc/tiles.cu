@@ -31,11 +31,6 @@ constexpr int PITCH = BS + 1; // shared-memory row pitch (elements): conflict-fr
 // ------------------------------------------------------------------------------------------------
 // small vector helpers
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-struct Vec4 {
-  T v[4];
-};
-
 __device__ __forceinline__ void ld_stream4(const float* p, float v[4]) {
   const float4 q = __ldcs(reinterpret_cast<const float4*>(p));
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
