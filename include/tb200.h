@@ -184,6 +184,16 @@ TB_API int tb_deaugment_merge(const void* pred, int dtype, const int32_t* xy, in
 TB_API int tb_normalize_crop(const void* image, const void* norm, int dtype, int K, int Hp, int Wp, int top, int left,
                       int H, int W, double eps, void* out, void* stream);
 
+/* SURVEY 8f rank 1, output side: class map / binary masks straight from the merged logits, so that one byte per
+ * pixel (instead of 4*K) crosses PCIe. Replaces `merged.argmax(dim=0).byte()` / `(merged.sigmoid() > thr).byte()`
+ * of the README loop (README.md:225; utils/torch_utils.py:144-159 to_numpy).
+ *   logits f32, K planes of n pixels, plane k at logits + k*plane_stride (so a band of rows of a [K,H,W] tensor works)
+ *   mode 0: out u8 [n]    = argmax over k (first maximum wins, NaN is maximal: torch.argmax); K <= 256
+ *   mode 1: out u8 [K][n] = sigmoid(logit) > threshold, plane k at out + k*out_plane_stride
+ * EXPERIMENTAL in round 1: compiled and exported, not yet validated on a GPU (tests opt-in, TB200_EXPERIMENTAL=1). */
+TB_API int tb_logits_to_labels(const float* logits, int K, int64_t plane_stride, int64_t n, int mode, float threshold,
+                        uint8_t* out, int64_t out_plane_stride, void* stream);
+
 /* Regular tile grid: tile (r,c), r < ny, c < nx sits at canvas (x,y) = (c*Sx, r*Sy). Where its A*K
  * prediction planes live:
  *   default            rows a*n_slots + slot of `pred`, slot = tile_slot ? tile_slot[r*nx+c] : r*nx+c

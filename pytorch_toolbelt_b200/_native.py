@@ -146,6 +146,7 @@ SIGNATURES = {
     ),
     "tb_dice_stats": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(DiceParams), _vp, _vp, _sz, _vp]),
     "tb_dice_loss_grad": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(DiceParams), _vp, _vp, _i, _vp, _vp, _vp]),
+    "tb_logits_to_labels": (_i, [_vp, _i, _i64, _i64, _i, _f, _vp, _i64, _vp]),
     "tb_focal_dice_fwd_bwd": (
         _i,
         [_vp, _vp, _i64, _i, _i64, C.POINTER(FocalParams), _vp, C.POINTER(DiceParams), _vp, _i, _f, _f, _vp, _vp, _vp, _sz, _vp],

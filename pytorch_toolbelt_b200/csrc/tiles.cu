@@ -779,6 +779,71 @@ __global__ void __launch_bounds__(kThreads) normalize_crop_kernel(const T* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// 6b. class map / binary masks from merged logits (output side: 1 byte per pixel leaves the GPU)
+// ------------------------------------------------------------------------------------------------
+// mode 0: out[i] = argmax_k logits[k][i] (first maximum wins, NaN counts as maximal: torch.argmax)
+// mode 1: out[k][i] = sigmoid(logits[k][i]) > thr
+template <int VW>
+__global__ void __launch_bounds__(kThreads) logits_to_labels_kernel(const float* __restrict__ logits, int K,
+                                                                     long long plane_stride, long long n, int mode,
+                                                                     float thr, unsigned char* __restrict__ out,
+                                                                     long long out_plane_stride) {
+  const long long nv = n / VW;
+  for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nv; v += (long long)gridDim.x * kThreads) {
+    const long long i0 = v * VW;
+    if (mode == 0) {
+      float best[VW];
+      int arg[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        best[e] = 0.f;
+        arg[e] = 0;
+      }
+      for (int k = 0; k < K; ++k) {
+        float x[VW];
+        if constexpr (VW == 4) {
+          const float4 q = __ldcs(reinterpret_cast<const float4*>(logits + (size_t)k * plane_stride + i0));
+          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+        } else {
+          x[0] = __ldcs(logits + (size_t)k * plane_stride + i0);
+        }
+#pragma unroll
+        for (int e = 0; e < VW; ++e) {
+          const bool take = (k == 0) || (x[e] > best[e]) || (x[e] != x[e] && best[e] == best[e]);
+          if (take) {
+            best[e] = x[e];
+            arg[e] = k;
+          }
+        }
+      }
+      if constexpr (VW == 4)
+        *reinterpret_cast<uchar4*>(out + i0) = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1],
+                                                           (unsigned char)arg[2], (unsigned char)arg[3]);
+      else
+        out[i0] = (unsigned char)arg[0];
+    } else {
+      for (int k = 0; k < K; ++k) {
+        float x[VW];
+        if constexpr (VW == 4) {
+          const float4 q = __ldcs(reinterpret_cast<const float4*>(logits + (size_t)k * plane_stride + i0));
+          x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+        } else {
+          x[0] = __ldcs(logits + (size_t)k * plane_stride + i0);
+        }
+        unsigned char m[VW];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) m[e] = (1.f / (1.f + expf(-x[e]))) > thr ? 1 : 0;
+        unsigned char* o = out + (size_t)k * out_plane_stride + i0;
+        if constexpr (VW == 4)
+          *reinterpret_cast<uchar4*>(o) = make_uchar4(m[0], m[1], m[2], m[3]);
+        else
+          o[0] = m[0];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 7. output-stationary fused de-augment + merge + normalise + crop
 // ------------------------------------------------------------------------------------------------
 struct MergeAllArgs {
@@ -1871,6 +1936,27 @@ int tb_normalize_crop(const void* image, const void* norm, int dtype, int K, int
   else
     return fail(TB_ERR_UNSUPPORTED, "tb_normalize_crop: dtype must be TB_F32 or TB_F64 (got %d)", dtype);
   TB_LAUNCH_CHECK("normalize_crop_kernel");
+  return TB_OK;
+}
+
+int tb_logits_to_labels(const float* logits, int K, int64_t plane_stride, int64_t n, int mode, float threshold,
+                        uint8_t* out, int64_t out_plane_stride, void* stream) {
+  TB_REQUIRE(logits && out, TB_ERR_ARG, "tb_logits_to_labels: null pointer");
+  TB_REQUIRE(K > 0 && n >= 0 && plane_stride >= n, TB_ERR_ARG, "tb_logits_to_labels: bad shape");
+  TB_REQUIRE(mode == 0 || mode == 1, TB_ERR_ARG, "tb_logits_to_labels: mode must be 0 (argmax) or 1 (sigmoid > threshold)");
+  TB_REQUIRE(mode == 1 || K <= 256, TB_ERR_UNSUPPORTED, "tb_logits_to_labels: argmax into uint8 needs K <= 256");
+  TB_REQUIRE(mode == 0 || out_plane_stride >= n, TB_ERR_ARG, "tb_logits_to_labels: bad out_plane_stride");
+  if (n == 0) return TB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec4 = (n % 4 == 0) && (plane_stride % 4 == 0) && aligned16(logits) && (reinterpret_cast<uintptr_t>(out) & 3) == 0 &&
+                    (mode == 0 || out_plane_stride % 4 == 0);
+  const long long items = vec4 ? n / 4 : n;
+  const int gx = (int)std::min<long long>((items + kThreads - 1) / kThreads, (long long)sm_count() * 16);
+  if (vec4)
+    logits_to_labels_kernel<4><<<gx, kThreads, 0, s>>>(logits, K, plane_stride, n, mode, threshold, out, out_plane_stride);
+  else
+    logits_to_labels_kernel<1><<<gx, kThreads, 0, s>>>(logits, K, plane_stride, n, mode, threshold, out, out_plane_stride);
+  TB_LAUNCH_CHECK("logits_to_labels_kernel");
   return TB_OK;
 }
 

@@ -319,6 +319,33 @@ class TiledInferenceEngine:
         args = (pred_ptr, grid_ref) + common
         return PreparedLaunch(N.lib().tb_merge_all, args, keep, result, device, "tb_merge_all")
 
+    # ------------------------------------------------------------------ output side
+    def labels(self, logits: torch.Tensor, mode: str = "argmax", threshold: float = 0.5,
+               out: Optional[torch.Tensor] = None, rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """uint8 class map [H,W] (``mode="argmax"``, = ``logits.argmax(0).byte()``) or uint8 masks [K,H,W]
+        (``mode="threshold"``, = ``(logits.sigmoid() > threshold).byte()``) from merged float32 logits [K,H,W];
+        ``rows=(i0,i1)`` restricts the work to those image rows (the pipelined host path converts band by band).
+        EXPERIMENTAL in round 1 (kernel not yet run on a GPU)."""
+        if mode not in ("argmax", "threshold"):
+            raise ValueError("mode must be 'argmax' or 'threshold'")
+        if not logits.is_cuda or logits.dtype != torch.float32 or logits.dim() != 3 or not logits.is_contiguous():
+            raise ValueError("labels() expects contiguous float32 CUDA logits [K,H,W]")
+        k, h, w = logits.shape
+        shape = (h, w) if mode == "argmax" else (k, h, w)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.uint8, device=logits.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != logits.device:
+            raise ValueError(f"out must be a contiguous uint8 tensor of shape {shape} on {logits.device}")
+        i0, i1 = rows if rows is not None else (0, h)
+        if not (0 <= i0 <= i1 <= h):
+            raise IndexError(f"rows {rows} outside [0,{h}]")
+        with torch.cuda.device(logits.device):
+            rc = N.lib().tb_logits_to_labels(
+                logits.data_ptr() + i0 * w * 4, k, h * w, (i1 - i0) * w, 0 if mode == "argmax" else 1, float(threshold),
+                out.data_ptr() + i0 * w, h * w, N.stream_ptr(logits.device))
+        N.check(rc, "tb_logits_to_labels")
+        return out
+
     # ------------------------------------------------------------------ whole pipeline
     @torch.no_grad()
     def predict(self, image: Union[np.ndarray, torch.Tensor], model: Callable[[torch.Tensor], torch.Tensor],
@@ -339,8 +366,12 @@ class TiledInferenceEngine:
     # ------------------------------------------------------------------ host -> host, pipelined over tile rows
     @torch.no_grad()
     def predict_to_host(self, image_host: torch.Tensor, model: Callable[[torch.Tensor], torch.Tensor],
-                        out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 2, layout: str = "HWC") -> torch.Tensor:
+                        out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 2, layout: str = "HWC",
+                        output: str = "logits", threshold: float = 0.5) -> torch.Tensor:
         """Pinned host image -> pinned host logits [K,H,W], software-pipelined over chunks of tile rows.
+
+        ``output="labels"`` / ``"mask"`` (experimental) convert every finished band with ``labels()`` on the GPU and
+        download uint8 [H,W] / [K,H,W] instead: 1 byte per pixel crosses PCIe instead of 4*K.
 
         For every chunk: (copy stream A) upload the image rows the chunk needs; (compute stream) slice+augment, model,
         merge the canvas rows that are now final (band mode of tb_merge_all_batched over the model outputs so far);
@@ -355,16 +386,27 @@ class TiledInferenceEngine:
         nx, ny, sw, sh, th, tw = self._grid_dims
         hp, wp = self.slicer.target_shape
         top = self.slicer.margin_top
+        if output not in ("logits", "labels", "mask"):
+            raise ValueError("output must be 'logits', 'labels' or 'mask'")
         if not image_host.is_pinned():
             image_host = image_host.pin_memory()
+        u8_shape = (h, w) if output == "labels" else (k, h, w)
         if out_host is None:
-            out_host = torch.empty((k, h, w), dtype=torch.float32).pin_memory()
+            out_host = (torch.empty((k, h, w), dtype=torch.float32) if output == "logits"
+                        else torch.empty(u8_shape, dtype=torch.uint8)).pin_memory()
+        elif output != "logits" and (tuple(out_host.shape) != u8_shape or out_host.dtype != torch.uint8):
+            raise ValueError(f"out_host must be uint8 {u8_shape} for output={output!r}")
         if not hasattr(self, "_pipe"):
             self._pipe = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
                               image=torch.empty(image_host.shape, dtype=image_host.dtype, device=dev),
                               out=torch.empty((k, h, w), dtype=torch.float32, device=dev))
         pipe = self._pipe
         image_dev, out_dev = pipe["image"], pipe["out"]
+        u8_dev = None
+        if output != "logits":
+            u8_dev = pipe.get("u8")
+            if u8_dev is None or tuple(u8_dev.shape) != u8_shape:
+                u8_dev = pipe["u8"] = torch.empty(u8_shape, dtype=torch.uint8, device=dev)
         if image_dev.shape != image_host.shape or image_dev.dtype != image_host.dtype:
             image_dev = pipe["image"] = torch.empty(image_host.shape, dtype=image_host.dtype, device=dev)
         main = torch.cuda.current_stream(dev)
@@ -391,12 +433,20 @@ class TiledInferenceEngine:
             self.merge(outputs, out=out_dev, rows=(merged_until, y_cur), tile_rows=(0, rb))
             o0, o1 = max(merged_until - top, 0), min(y_cur - top, h)
             if o1 > o0:
+                if u8_dev is not None:  # finished band -> class map / masks on the GPU, 1 byte per pixel to download
+                    self.labels(out_dev, "argmax" if output == "labels" else "threshold", threshold, out=u8_dev, rows=(o0, o1))
                 ev2 = torch.cuda.Event()
                 ev2.record(main)
                 pipe["d2h"].wait_event(ev2)
                 with torch.cuda.stream(pipe["d2h"]):
-                    for kk in range(k):  # per-channel row blocks are contiguous on both sides: truly async copies
-                        out_host[kk, o0:o1].copy_(out_dev[kk, o0:o1], non_blocking=True)
+                    if output == "logits":
+                        for kk in range(k):  # per-channel row blocks are contiguous on both sides: truly async copies
+                            out_host[kk, o0:o1].copy_(out_dev[kk, o0:o1], non_blocking=True)
+                    elif output == "labels":
+                        out_host[o0:o1].copy_(u8_dev[o0:o1], non_blocking=True)
+                    else:
+                        for kk in range(k):
+                            out_host[kk, o0:o1].copy_(u8_dev[kk, o0:o1], non_blocking=True)
             merged_until = y_cur
         main.wait_stream(pipe["d2h"])
         self._keepalive_outputs = outputs  # kernels of this call may still be reading them

@@ -64,3 +64,56 @@ def test_joint_falls_back_to_two_kernels_when_not_fusable():
     x2 = x.clone().requires_grad_(True)
     (L.BinaryFocalLoss()(x2, labels) + L.DiceLoss("multiclass")(x2, labels)).backward()
     torch.testing.assert_close(x1.grad, x2.grad)
+
+
+@pytest.mark.parametrize("shape", [(4, 96, 128), (3, 37, 53), (1, 16, 20), (7, 64, 64)])
+def test_logits_to_labels_matches_torch(shape):
+    from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine
+
+    k, h, w = shape
+    eng = TiledInferenceEngine((h, w, 3), 16, 16, channels=k, weight="mean")
+    g = torch.Generator().manual_seed(9)
+    logits = (torch.randn(k, h, w, generator=g) * 3)
+    logits[:, 1, 2] = 1.5  # a tie: the first maximum wins
+    logits = logits.cuda()
+    assert torch.equal(eng.labels(logits), logits.argmax(dim=0).to(torch.uint8))
+    want = (logits.sigmoid() > 0.3).to(torch.uint8)
+    got = eng.labels(logits, mode="threshold", threshold=0.3)
+    boundary = (logits.sigmoid() - 0.3).abs() < 1e-6  # 1-ulp differences of the sigmoid may flip exactly-at-threshold pixels
+    assert torch.equal(got[~boundary], want[~boundary])
+    # band by band into one buffer == whole image
+    out = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    cuts = [0, h // 3, h // 2, h]
+    for a, b in zip(cuts, cuts[1:]):
+        eng.labels(logits, out=out, rows=(a, b))
+    assert torch.equal(out, logits.argmax(dim=0).to(torch.uint8))
+
+
+def test_predict_to_host_labels_and_masks():
+    import numpy as np
+
+    from pytorch_toolbelt_b200.inference.engine import TiledInferenceEngine
+
+    rng = np.random.default_rng(2)
+    image = rng.integers(0, 256, (600, 520, 3)).astype(np.uint8)
+    k = 3
+    eng = TiledInferenceEngine(image.shape, 128, 64, channels=k, weight="pyramid", tta="flips")
+    wm = torch.randn(k, 3, generator=torch.Generator().manual_seed(0)).cuda()
+
+    def model(x):
+        return torch.einsum("kc,bchw->bkhw", wm, x) * 0.02 - 1.0
+
+    logits = eng.predict(eng.to_device(image), model, batch_size=8)
+    host = torch.from_numpy(image).pin_memory()
+    labels = eng.predict_to_host(host, model, output="labels")
+    assert labels.dtype == torch.uint8 and tuple(labels.shape) == (600, 520)
+    torch.cuda.synchronize()
+    assert torch.equal(labels, logits.argmax(dim=0).to(torch.uint8).cpu())
+    masks = eng.predict_to_host(host, model, output="mask", threshold=0.4)
+    torch.cuda.synchronize()
+    want = (logits.sigmoid() > 0.4).to(torch.uint8).cpu()
+    boundary = ((logits.sigmoid() - 0.4).abs() < 1e-6).cpu()
+    assert torch.equal(masks[~boundary], want[~boundary])
+    again = eng.predict_to_host(host, model)  # the default path is untouched by the option
+    torch.cuda.synchronize()
+    assert torch.equal(again, logits.cpu())
