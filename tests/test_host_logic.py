@@ -151,3 +151,59 @@ def test_d4_view_codes_form_the_group():
     assert F._compose(F.CODE_ROT90_CCW, F.CODE_TRANSPOSE) == F.CODE_FLIPLR
     assert F._compose(F.CODE_ROT90_CW, F.CODE_TRANSPOSE) == F.CODE_FLIPUD
     assert F._compose(F.CODE_ROT180, F.CODE_TRANSPOSE) == F.CODE_ANTITRANSPOSE
+
+
+def test_prepared_launch_falls_back_once_on_unsupported():
+    from pytorch_toolbelt_b200.inference.engine import PreparedLaunch
+
+    class HostLaunch(PreparedLaunch):  # no CUDA device to select on this host
+        __slots__ = ()
+
+        def _call(self):
+            return self.fn(*self.args)
+
+    calls = []
+
+    def first(*args):
+        calls.append(("first", args))
+        return -2  # TB_ERR_UNSUPPORTED: nothing launched
+
+    def second(*args):
+        calls.append(("second", args))
+        return 0
+
+    plan = HostLaunch(first, (1, 2), [], "result", None, "first", fallback=lambda: (second, (3,), "second"))
+    assert plan.run() == "result" and plan.run() == "result"
+    assert [c[0] for c in calls] == ["first", "second", "second"] and calls[1][1] == (3,)
+    with pytest.raises(N.TB200Error):
+        HostLaunch(first, (), [], None, None, "tb_merge_all_batched").run()
+
+
+def test_clock_sampler_summary_and_fallbacks():
+    from pytorch_toolbelt_b200.utils.clocks import ClockSampler
+
+    s = ClockSampler()
+    assert s.summary()["reasons"] == ["unavailable"] and s.summary()["samples"] == 0
+    s.sm, s.max_mhz, s.source = [1965.0, 1950.0, 1965.0], 1965.0, "nvml"
+    s.reasons.add("sw_power_cap")
+    out = s.summary()
+    assert out == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3, "source": "nvml"}
+    with ClockSampler() as live:  # no NVML / nvidia-smi on the build host: must degrade, not raise
+        pass
+    assert live.summary()["samples"] >= 0
+
+
+def test_joint_loss_fusability_rules():
+    import pytorch_toolbelt_b200.losses as L
+
+    x, t = torch.zeros(2, 3, 8, 8), torch.zeros(2, 3, 8, 8)
+    labels = torch.zeros(2, 8, 8, dtype=torch.long)
+    assert L.BinaryFocalDiceLoss(L.BinaryFocalLoss(), L.DiceLoss("multilabel")).fusable(x, t)
+    assert L.BinaryFocalDiceLoss(L.BinaryFocalLoss(reduction="sum"), L.JaccardLoss("binary")).fusable(x, t)
+    assert not L.BinaryFocalDiceLoss(L.BinaryFocalLoss(), L.DiceLoss("multiclass")).fusable(x, labels)
+    assert not L.BinaryFocalDiceLoss(L.BinaryFocalLoss(normalized=True), L.DiceLoss("multilabel")).fusable(x, t)
+    assert not L.BinaryFocalDiceLoss(L.BinaryFocalLoss(reduction="none"), L.DiceLoss("multilabel")).fusable(x, t)
+    assert not L.BinaryFocalDiceLoss(L.BinaryFocalLoss(), L.DiceLoss("multilabel", from_logits=False)).fusable(x, t)
+    assert not L.BinaryFocalDiceLoss(L.BinaryFocalLoss(class_weights=[1.0, 2.0, 3.0]), L.DiceLoss("binary")).fusable(x, t)
+    with pytest.raises(TypeError):
+        L.BinaryFocalDiceLoss(L.DiceLoss("binary"), L.DiceLoss("binary"))
