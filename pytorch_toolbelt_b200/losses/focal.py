@@ -1,4 +1,12 @@
-"""BinaryFocalLoss / CrossEntropyFocalLoss / FocalLoss: drop-in for ``pytorch_toolbelt/losses/focal.py``."""
+"""Focal-loss modules over the fused kernels: ``BinaryFocalLoss`` (sigmoid or channel-softmax focal term on dense or
+label targets), ``CrossEntropyFocalLoss`` (softmax focal term, ``nn.CrossEntropyLoss``-style targets) and the
+deprecated ``FocalLoss`` alias.
+
+Constructor arguments, defaults, public attributes and ``forward`` conventions are those of
+``pytorch_toolbelt/losses/focal.py:13-166``; nothing is computed here -- ``forward`` hands the options to
+``losses.functional`` which launches ``tb_focal_fwd_bwd`` / ``tb_softmax_focal_fwd_bwd`` (loss and gradient in one
+pass; the one-hot expansion of label targets, focal.py:94-105, happens inside the kernel).
+"""
 from typing import Optional
 
 import torch
@@ -9,96 +17,78 @@ from .functional import _focal_from_labels, focal_loss_with_logits, softmax_foca
 
 __all__ = ["CrossEntropyFocalLoss", "BinaryFocalLoss", "FocalLoss"]
 
+_BINARY_OPTIONS = ("alpha", "gamma", "ignore_index", "reduction", "normalized", "reduced_threshold", "activation",
+                   "softmax_dim")
+_MULTICLASS_OPTIONS = ("gamma", "reduction", "normalized", "reduced_threshold", "ignore_index")
+
+
+def _as_weight_buffer(class_weights) -> Optional[Tensor]:
+    if class_weights is None or torch.is_tensor(class_weights):
+        return class_weights
+    return torch.tensor(list(class_weights), dtype=torch.float32)
+
 
 class BinaryFocalLoss(nn.Module):
-    __constants__ = ["alpha", "gamma", "reduction", "ignore_index", "normalized", "reduced_threshold", "activation"]
+    """Focal loss for binary / multi-label problems.
 
-    def __init__(
-        self,
-        alpha: Optional[float] = None,
-        gamma: float = 2.0,
-        ignore_index: Optional[int] = None,
-        reduction: str = "mean",
-        normalized: bool = False,
-        reduced_threshold: Optional[float] = None,
-        activation: str = "sigmoid",
-        softmax_dim: Optional[int] = None,
-        class_weights: Optional[Tensor] = None,
-    ):
-        """
-        :param alpha: Prior probability of having positive value in target.
-        :param gamma: Power factor for dampening weight (focal strength).
-        :param ignore_index: targets equal to ignore_index do not contribute to the loss.
-        :param reduced_threshold: switch to reduced focal loss (use reduction="sum" with it, as upstream advises).
-        :param activation: "sigmoid" or "softmax" (then softmax_dim must be 1).
-        """
+    ``alpha``: prior of the positive class (None = no class balancing); ``gamma``: focusing power; ``ignore_index``:
+    target value whose elements contribute nothing; ``reduction``: "mean" | "sum" | "batchwise_mean" | "none";
+    ``normalized``: divide by the sum of the focal terms; ``reduced_threshold``: reduced focal loss (upstream advises
+    ``reduction="sum"`` with it); ``activation``: "sigmoid", or "softmax" with ``softmax_dim=1``; ``class_weights``:
+    per-channel multipliers ``[C]``.
+    """
+
+    __constants__ = list(_BINARY_OPTIONS)
+
+    def __init__(self, alpha: Optional[float] = None, gamma: float = 2.0, ignore_index: Optional[int] = None,
+                 reduction: str = "mean", normalized: bool = False, reduced_threshold: Optional[float] = None,
+                 activation: str = "sigmoid", softmax_dim: Optional[int] = None,
+                 class_weights: Optional[Tensor] = None):
         super().__init__()
-        self.alpha = alpha
-        self.gamma = gamma
-        self.ignore_index = ignore_index
-        self.reduction = reduction
-        self.normalized = normalized
-        self.reduced_threshold = reduced_threshold
-        self.activation = activation
-        self.softmax_dim = softmax_dim
-        if class_weights is not None and not torch.is_tensor(class_weights):
-            class_weights = torch.tensor(list(class_weights), dtype=torch.float32)
-        self.register_buffer("class_weights", class_weights, persistent=False)
+        given = dict(alpha=alpha, gamma=gamma, ignore_index=ignore_index, reduction=reduction, normalized=normalized,
+                     reduced_threshold=reduced_threshold, activation=activation, softmax_dim=softmax_dim)
+        for name in _BINARY_OPTIONS:
+            setattr(self, name, given[name])
+        self.register_buffer("class_weights", _as_weight_buffer(class_weights), persistent=False)
+
+    def _options(self) -> dict:
+        return {name: getattr(self, name) for name in _BINARY_OPTIONS}
 
     def __repr__(self):
-        cw = None if self.class_weights is None else self.class_weights.tolist()
-        return (
-            f"{self.__class__.__name__}(alpha={self.alpha}, gamma={self.gamma}, ignore_index={self.ignore_index}, "
-            f"reduction={self.reduction}, normalized={self.normalized}, reduced_threshold={self.reduced_threshold}, "
-            f"activation={self.activation}, softmax_dim={self.softmax_dim}, class_weights={cw})"
-        )
+        shown = ", ".join(f"{name}={value}" for name, value in self._options().items())
+        weights = None if self.class_weights is None else self.class_weights.tolist()
+        return f"{type(self).__name__}({shown}, class_weights={weights})"
 
     def forward(self, inputs: Tensor, targets: Tensor) -> Tensor:
-        """
-        :param inputs: [B,C,H,W] logits
-        :param targets: [B,C,H,W] (same shape) or [B,H,W] long class indices, one-hot encoded w.r.t. ignore_index
-        """
-        kw = dict(alpha=self.alpha, gamma=self.gamma, reduced_threshold=self.reduced_threshold, reduction=self.reduction,
-                  normalized=self.normalized, ignore_index=self.ignore_index, activation=self.activation, eps=1e-6)
-        if len(targets.shape) + 1 == len(inputs.shape):
-            if self.activation != "sigmoid" and self.softmax_dim != 1:
-                raise NotImplementedError("activation='softmax' is implemented for softmax_dim=1")
-            return _focal_from_labels(inputs, targets, self.class_weights, **kw)
-        kw.pop("eps")
-        return focal_loss_with_logits(inputs, targets, softmax_dim=self.softmax_dim, class_weights=self.class_weights, **kw)
+        """``inputs`` [B,C,*] logits; ``targets`` of the same shape, or [B,*] integer labels that are one-hot encoded
+        with respect to ``ignore_index`` (inside the kernel)."""
+        options = self._options()
+        label_targets = targets.dim() + 1 == inputs.dim()
+        if not label_targets:
+            return focal_loss_with_logits(inputs, targets, class_weights=self.class_weights, **options)
+        if self.activation != "sigmoid" and self.softmax_dim != 1:
+            raise NotImplementedError("activation='softmax' is implemented for softmax_dim=1")
+        options.pop("softmax_dim")
+        return _focal_from_labels(inputs, targets, self.class_weights, eps=1e-6, **options)
 
 
 class CrossEntropyFocalLoss(nn.Module):
-    """Focal loss for multi-class problems (softmax focal term); targets have one dim less, like nn.CrossEntropyLoss."""
+    """Multi-class focal loss whose focal term comes from the channel softmax; ``targets`` are class indices with one
+    dimension less than ``inputs``; ``ignore_index`` (default -100) marks pixels that contribute nothing."""
 
-    def __init__(
-        self,
-        gamma: float = 2.0,
-        reduction: str = "mean",
-        normalized: bool = False,
-        reduced_threshold: Optional[float] = None,
-        ignore_index: int = -100,
-        class_weights: Optional[Tensor] = None,
-    ):
+    def __init__(self, gamma: float = 2.0, reduction: str = "mean", normalized: bool = False,
+                 reduced_threshold: Optional[float] = None, ignore_index: int = -100,
+                 class_weights: Optional[Tensor] = None):
         super().__init__()
-        self.gamma = gamma
-        self.reduction = reduction
-        self.reduced_threshold = reduced_threshold
-        self.normalized = normalized
-        self.ignore_index = ignore_index
+        given = dict(gamma=gamma, reduction=reduction, normalized=normalized, reduced_threshold=reduced_threshold,
+                     ignore_index=ignore_index)
+        for name in _MULTICLASS_OPTIONS:
+            setattr(self, name, given[name])
         self.register_buffer("class_weights", class_weights, persistent=False)
 
     def forward(self, inputs: Tensor, targets: Tensor) -> Tensor:
-        return softmax_focal_loss_with_logits(
-            inputs,
-            targets,
-            gamma=self.gamma,
-            reduction=self.reduction,
-            normalized=self.normalized,
-            reduced_threshold=self.reduced_threshold,
-            ignore_index=self.ignore_index,
-            class_weights=self.class_weights,
-        )
+        options = {name: getattr(self, name) for name in _MULTICLASS_OPTIONS}
+        return softmax_focal_loss_with_logits(inputs, targets, class_weights=self.class_weights, **options)
 
 
 @pytorch_toolbelt_deprecated("Class FocalLoss is deprecated. Please use CrossEntropyFocalLoss instead.")
