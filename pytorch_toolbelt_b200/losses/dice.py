@@ -108,50 +108,44 @@ class _RegionLoss(torch.autograd.Function):
         return grad, None, None
 
 
-class DiceLoss(_Loss):
-    """Dice loss for image segmentation: binary, multiclass and multilabel (reference dice.py:18-131)."""
+class _RegionLossModule(_Loss):
+    """Shared module body of DiceLoss / JaccardLoss: holds the options, launches the two fused kernels."""
 
-    def __init__(
-        self,
-        mode: str,
-        classes: List[int] = None,
-        log_loss=False,
-        from_logits=True,
-        smooth: float = 0.0,
-        ignore_index=None,
-        eps=1e-7,
-    ):
-        """
-        :param mode: 'binary', 'multiclass' or 'multilabel'
-        :param classes: optional list of classes that contribute to the loss (default: all channels). Implements the
-            documented intent; the reference's own handling of this argument is broken.
-        :param log_loss: if True the loss is ``-log(dice)``, otherwise ``1 - dice``
-        :param from_logits: if True the input is raw logits
-        :param ignore_index: label of ignored pixels
-        """
-        assert mode in {BINARY_MODE, MULTILABEL_MODE, MULTICLASS_MODE}
-        super(DiceLoss, self).__init__()
-        self.mode = mode
+    _jaccard = False
+
+    def __init__(self, mode, classes, log_loss, from_logits, smooth, eps, ignore_index):
+        if mode not in _MODE_CODE:
+            raise AssertionError(f"mode must be one of {sorted(_MODE_CODE)}, got {mode!r}")
+        super().__init__()
         if classes is not None:
             assert mode != BINARY_MODE, "Masking classes is not supported with mode=binary"
             classes = [int(c) for c in (classes.tolist() if torch.is_tensor(classes) else classes)]
-        self.classes = classes
-        self.from_logits = from_logits
-        self.smooth = smooth
-        self.eps = eps
-        self.ignore_index = ignore_index
-        self.log_loss = log_loss
+        self.mode, self.classes = mode, classes
+        self.log_loss, self.from_logits = log_loss, from_logits
+        self.smooth, self.eps, self.ignore_index = smooth, eps, ignore_index
+
+    def _sync_cfg(self) -> dict:
+        """Overridden by the data-parallel variants (distributed/losses.py) to request the statistics all-reduce."""
+        return {}
 
     def forward(self, y_pred: Tensor, y_true: Tensor) -> Tensor:
-        """
-        :param y_pred: NxCxHxW
-        :param y_true: NxHxW (multiclass) or NxCxHxW / Nx1xHxW
-        """
+        """``y_pred`` [N,C,*]; ``y_true`` [N,*] labels (multiclass) or [N,C,*] / [N,1,*] dense targets."""
         assert y_true.size(0) == y_pred.size(0)
-        cfg = dict(jaccard=False, mode=self.mode, classes=self.classes, log_loss=self.log_loss,
+        cfg = dict(jaccard=self._jaccard, mode=self.mode, classes=self.classes, log_loss=self.log_loss,
                    from_logits=self.from_logits, smooth=self.smooth, eps=self.eps, ignore_index=self.ignore_index)
         cfg.update(self._sync_cfg())
         return _RegionLoss.apply(y_pred, y_true, cfg)
 
-    def _sync_cfg(self) -> dict:
-        return {}
+
+class DiceLoss(_RegionLossModule):
+    """Dice loss for image segmentation: binary, multiclass and multilabel (reference dice.py:18-131).
+
+    ``mode``: 'binary' | 'multiclass' | 'multilabel'; ``classes``: optional list of channels that contribute (the
+    documented intent -- the reference's own handling of this argument is broken); ``log_loss``:
+    ``-log(dice)`` instead of ``1 - dice``; ``from_logits``: the input is raw logits; ``ignore_index``: label of
+    ignored pixels.
+    """
+
+    def __init__(self, mode: str, classes: List[int] = None, log_loss=False, from_logits=True, smooth: float = 0.0,
+                 ignore_index=None, eps=1e-7):
+        super().__init__(mode, classes, log_loss, from_logits, smooth, eps, ignore_index)
