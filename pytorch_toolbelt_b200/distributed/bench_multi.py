@@ -26,8 +26,6 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # stdout carries exactly one JSON line (rank 0): NCCL's own banner / debug lines go to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 
     H, W, Cin, T, S, K = (CFG[k] for k in ("H", "W", "Cin", "T", "S", "K"))
