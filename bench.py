@@ -51,15 +51,37 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference's torch-CPU path, restated by the oracle (the reference itself is
-# pure Python under /root/reference and cannot travel to the GPU box)
+# reference arm / cpu_baseline: the reference's own torch-CPU path. Preferred: the UNMODIFIED reference installed under
+# baseline/_ref (baseline/install_ref.sh; git-ignored, shipped to the GPU box), driven through ImageSlicer / tta.* /
+# TileMerger by baseline/reference_arm.py (kind "reference"). Fallback when that install is absent: the oracle's
+# restatement (kind "port"; bit-identical results, checked in tests/test_reference_install.py).
 # --------------------------------------------------------------------------------------------------------------
+def reference_loop():
+    """-> (callable with tiled_inference_cpu's signature, kind)"""
+    try:
+        from baseline import reference_arm as RA
+
+        if RA.available():
+            RA.load()
+
+            def run(image, tile, step, K, weight="pyramid", group="none", batch_size=8, timings=None, max_tiles=None,
+                    device="cpu"):
+                return RA.tiled_inference(image, tile, step, K, weight=weight, group=None if group == "none" else group,
+                                          batch_size=batch_size, timings=timings, max_tiles=max_tiles, device=device)
+
+            return run, "reference"
+    except Exception as e:  # a broken install must not take the bench down: fall back to the port and say so
+        sys.stderr.write(f"[bench] reference install unusable ({e!r}); using the oracle port\n")
+    from oracle import pipeline as OP
+
+    return OP.tiled_inference_cpu, "port"
+
+
 def cpu_reference_sample(sample_tiles: int, threads: int = 0):
     """Time the oracle's restatement of the reference loop (split -> augment -> stand-in model -> de-augment ->
     integrate -> merge) on a bounded sample of cfg 2: the first `sample_tiles` of the 361 tiles (the whole-image
     split and the full-canvas normalise are included in full). Returns (MP/s engine-only, MP/s with model, info)."""
-    from oracle import pipeline as OP
-
+    loop, kind = reference_loop()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     threads = threads or best_cpu_threads(cores)
     torch.set_num_threads(threads)
@@ -67,7 +89,7 @@ def cpu_reference_sample(sample_tiles: int, threads: int = 0):
     image = rng.integers(0, 256, (CFG["H"], CFG["W"], CFG["Cin"])).astype(np.uint8)
     timings = {}
     t0 = time.perf_counter()
-    OP.tiled_inference_cpu(image, CFG["T"], CFG["S"], CFG["K"], weight=CFG["weight"], group=CFG["tta"], batch_size=8,
+    loop(image, CFG["T"], CFG["S"], CFG["K"], weight=CFG["weight"], group=CFG["tta"], batch_size=8,
                            timings=timings, max_tiles=sample_tiles)
     wall = time.perf_counter() - t0
     n_total = 361
@@ -81,9 +103,11 @@ def cpu_reference_sample(sample_tiles: int, threads: int = 0):
     info = {
         "cores": threads,
         "host_cores": cores,
-        "kind": "port",
-        "sample": f"first {sample_tiles} of 361 tiles of cfg2 (d4, batch 8) through oracle/pipeline.py "
-                  f"(torch-CPU restatement of the reference loop); per-tile stages scaled x{1 / frac:.2f}, "
+        "kind": kind,
+        "sample": f"first {sample_tiles} of 361 tiles of cfg2 (d4, batch 8) through "
+                  + ("the installed reference (baseline/_ref: ImageSlicer/tta.d4_*/TileMerger on torch-CPU)" if kind == "reference"
+                     else "oracle/pipeline.py (torch-CPU restatement of the reference loop)")
+                  + f"; per-tile stages scaled x{1 / frac:.2f}, "
                   f"whole-image split+normalise in full; wall {wall:.1f}s",
         "stage_seconds_sample": {k: round(v, 3) for k, v in timings.items()},
         "cpu_model": _cpu_model(),
@@ -101,18 +125,17 @@ def best_cpu_threads(cores: int) -> int:
     reference. Probe a few pool sizes on a tiny sample and keep the fastest."""
     if cores in _BEST_THREADS:
         return _BEST_THREADS[cores]
-    from oracle import pipeline as OP
-
+    loop, _ = reference_loop()
     rng = np.random.default_rng(1)
     image = rng.integers(0, 256, (1536, 1536, 3)).astype(np.uint8)
     best, best_t = cores, float("inf")
     for th in sorted({t for t in (8, 16, 32, 64, cores) if t <= cores} or {cores}):
         torch.set_num_threads(th)
-        OP.tiled_inference_cpu(image, 512, 256, 4, group="d4", batch_size=8, max_tiles=8)
+        loop(image, 512, 256, 4, group="d4", batch_size=8, max_tiles=8)
         dt = float("inf")
         for _ in range(2):
             t0 = time.perf_counter()
-            OP.tiled_inference_cpu(image, 512, 256, 4, group="d4", batch_size=8, max_tiles=25)
+            loop(image, 512, 256, 4, group="d4", batch_size=8, max_tiles=25)
             dt = min(dt, time.perf_counter() - t0)
         if dt < best_t:
             best, best_t = th, dt

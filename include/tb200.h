@@ -190,7 +190,7 @@ TB_API int tb_normalize_crop(const void* image, const void* norm, int dtype, int
  *   logits f32, K planes of n pixels, plane k at logits + k*plane_stride (so a band of rows of a [K,H,W] tensor works)
  *   mode 0: out u8 [n]    = argmax over k (first maximum wins, NaN is maximal: torch.argmax); K <= 256
  *   mode 1: out u8 [K][n] = sigmoid(logit) > threshold, plane k at out + k*out_plane_stride
- * EXPERIMENTAL in round 1: compiled and exported, not yet validated on a GPU (tests opt-in, TB200_EXPERIMENTAL=1). */
+ * Validated on a B200 in round 2 (tests/test_joint_labels_gpu.py). */
 TB_API int tb_logits_to_labels(const float* logits, int K, int64_t plane_stride, int64_t n, int mode, float threshold,
                         uint8_t* out, int64_t out_plane_stride, void* stream);
 
@@ -313,7 +313,7 @@ TB_API int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t 
  * w_dice * region, and its gradient, in two passes over (x, t) and one gradient write.
  * Restrictions (TB_ERR_UNSUPPORTED otherwise): focal sigmoid, not normalised, reduction MEAN or SUM; region mode
  * binary / multilabel with from_logits. loss_out f32 [3] = (total, focal term, region term), unweighted terms.
- * EXPERIMENTAL in round 1: compiled and exported, not yet validated on a GPU (tests are opt-in, TB200_EXPERIMENTAL=1). */
+ * Validated on a B200 in round 2 (tests/test_joint_labels_gpu.py). */
 TB_API int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int64_t inner, const tb_focal_params* fp,
                           const float* class_w, const tb_dice_params* dp, const int32_t* classes, int n_classes,
                           float w_focal, float w_dice, float* loss_out, float* grad, void* ws, size_t ws_bytes,

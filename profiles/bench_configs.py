@@ -29,7 +29,10 @@ CFGS = {
     "cfg5_table_weight": dict(H=20000, W=20000, Cin=1, T=1024, S=512, K=1, tta=None, weight="gaussian", analytic=False),
 }
 out = {"peak_gbs": peak}
+sel = sys.argv[1:] or list(CFGS)
 for name, c in CFGS.items():
+    if name not in sel:
+        continue
     H, W, Cin, T, S, K = c["H"], c["W"], c["Cin"], c["T"], c["S"], c["K"]
     rng = np.random.default_rng(0)
     image = torch.from_numpy(rng.integers(0, 256, (H, W, Cin)).astype(np.uint8)).to(dev)

@@ -324,8 +324,7 @@ class TiledInferenceEngine:
                out: Optional[torch.Tensor] = None, rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """uint8 class map [H,W] (``mode="argmax"``, = ``logits.argmax(0).byte()``) or uint8 masks [K,H,W]
         (``mode="threshold"``, = ``(logits.sigmoid() > threshold).byte()``) from merged float32 logits [K,H,W];
-        ``rows=(i0,i1)`` restricts the work to those image rows (the pipelined host path converts band by band).
-        EXPERIMENTAL in round 1 (kernel not yet run on a GPU)."""
+        ``rows=(i0,i1)`` restricts the work to those image rows (the pipelined host path converts band by band)."""
         if mode not in ("argmax", "threshold"):
             raise ValueError("mode must be 'argmax' or 'threshold'")
         if not logits.is_cuda or logits.dtype != torch.float32 or logits.dim() != 3 or not logits.is_contiguous():
@@ -370,7 +369,7 @@ class TiledInferenceEngine:
                         output: str = "logits", threshold: float = 0.5) -> torch.Tensor:
         """Pinned host image -> pinned host logits [K,H,W], software-pipelined over chunks of tile rows.
 
-        ``output="labels"`` / ``"mask"`` (experimental) convert every finished band with ``labels()`` on the GPU and
+        ``output="labels"`` / ``"mask"`` convert every finished band with ``labels()`` on the GPU and
         download uint8 [H,W] / [K,H,W] instead: 1 byte per pixel crosses PCIe instead of 4*K.
 
         For every chunk: (copy stream A) upload the image rows the chunk needs; (compute stream) slice+augment, model,

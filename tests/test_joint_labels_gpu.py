@@ -1,15 +1,10 @@
-"""Opt-in parity tests for kernels that were written after the round's GPU budget was spent: compiled, exported,
-but never run on a GPU yet. Enable with TB200_EXPERIMENTAL=1 (first thing to do in the next round); until they have
-passed once on a B200 they must not be able to turn the default suite red."""
-import os
-
+"""Parity tests for the joint focal+dice kernel (BASELINE config 3 as stated), the logits->labels output kernel and the
+uint8 download path of predict_to_host. First run on a B200 in round 2 (10 passed; compute-sanitizer memcheck: 0 errors,
+profiles/r2_validation.md), since then part of the default -m gpu suite."""
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("TB200_EXPERIMENTAL") != "1", reason="unvalidated kernels: set TB200_EXPERIMENTAL=1"),
-]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode,shape", [("multilabel", (4, 3, 64, 48)), ("binary", (5, 1, 33, 31)), ("multilabel", (2, 4, 17, 19)),
