@@ -1564,11 +1564,12 @@ template <int TTA, bool LINEAR, int MAXB, int NG>
 static cudaError_t launch_merge_all_tma_impl2(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
   const size_t smem = tma_smem_bytes(NV, true);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(merge_all_tma_kernel<TTA, LINEAR, MAXB, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   const int grid = std::min((nblocks + NG - 1) / NG, sm_count());  // persistent: one CTA per SM
   merge_all_tma_kernel<TTA, LINEAR, MAXB, NG><<<grid, kTmaThreads * NG, smem, s>>>(a, maps, nblocks);
@@ -1595,16 +1596,17 @@ template <int TTA, bool LINEAR, bool SCATTER>
 static cudaError_t launch_tile_deaug_tma_impl(const TileTmaArgs& a, const TmaMaps<1>& maps, int nblocks, cudaStream_t s) {
   constexpr int NV = Views<TTA>::count;
   const size_t smem = tma_smem_bytes(NV);
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
+  static int ctas_per_sm_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!ctas_per_sm_dev[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tile_deaug_tma_kernel<TTA, LINEAR, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_deaug_tma_kernel<TTA, LINEAR, SCATTER>, kTmaThreads, smem);
     if (e != cudaSuccess) return e;
-    ctas_per_sm = n > 0 ? n : 1;
+    ctas_per_sm_dev[dev] = n > 0 ? n : 1;
   }
-  const int grid = std::min(nblocks, sm_count() * ctas_per_sm);
+  const int grid = std::min(nblocks, sm_count() * ctas_per_sm_dev[dev]);
   tile_deaug_tma_kernel<TTA, LINEAR, SCATTER><<<grid, kTmaThreads, smem, s>>>(a, maps, nblocks);
   return cudaGetLastError();
 }

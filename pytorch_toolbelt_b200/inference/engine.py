@@ -449,4 +449,7 @@ class TiledInferenceEngine:
             merged_until = y_cur
         main.wait_stream(pipe["d2h"])
         self._keepalive_outputs = outputs  # kernels of this call may still be reading them
+        # the result is a HOST tensor: do not hand it back before the asynchronous downloads have landed (stream order
+        # alone does not hold the host back). Only the d2h stream is waited for, not the whole device.
+        pipe["d2h"].synchronize()
         return out_host

@@ -94,6 +94,7 @@ class _RegionLoss(torch.autograd.Function):
                                            N.ptr(grad), stream)
             N.check(rc, "tb_dice_loss_grad")
         ctx.stored_grad, ctx.origin, ctx.x_shape, ctx.x_dtype = grad, origin, y_pred.shape, y_pred.dtype
+        ctx.grad_mul = float(cfg.get("grad_mul", 1.0))
         return out if origin.type == "cuda" else out.to(origin)
 
     @staticmethod
@@ -102,6 +103,8 @@ class _RegionLoss(torch.autograd.Function):
         if grad is None:
             raise RuntimeError("backward called twice on a fused loss; recompute the loss instead of retaining the graph")
         ctx.stored_grad = None
+        if ctx.grad_mul != 1.0:  # data-parallel variants under DDP gradient AVERAGING (distributed/losses.py)
+            upstream = upstream * ctx.grad_mul
         grad = K.scale_stored_grad(grad, upstream).reshape(ctx.x_shape).to(ctx.x_dtype)
         if ctx.origin.type != "cuda":
             grad = grad.to(ctx.origin)

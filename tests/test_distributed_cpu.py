@@ -158,3 +158,44 @@ def test_data_parallel_loss_reductions(tmp_path):
     world = 2
     mp.spawn(_loss_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
+
+
+def _grad_convention_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import losses_oracle as LO
+        from pytorch_toolbelt_b200.distributed.losses import global_mean
+
+        g = torch.Generator().manual_seed(21)
+        feats = torch.randn(2 * world, 3, 8, 8, generator=g)
+        t = (torch.rand(2 * world, 3, 8, 8, generator=g) < 0.3).float()
+        w0 = torch.tensor([0.7, -1.3, 2.1]).view(1, 3, 1, 1)
+        mine = slice(2 * rank, 2 * rank + 2)
+        # single-process whole-batch parameter gradient
+        w = w0.clone().requires_grad_(True)
+        LO.focal_sigmoid(feats * w, t, alpha=None).backward()
+        whole = w.grad.clone()
+        for convention in ("sum", "ddp_mean"):
+            wl = w0.clone().requires_grad_(True)
+            loss = global_mean(LO.focal_sigmoid(feats[mine] * wl, t[mine], alpha=None), grad_reduction=convention)
+            loss.backward()
+            gsum = wl.grad.clone()
+            dist.all_reduce(gsum)  # SUM over ranks
+            reduced = gsum if convention == "sum" else gsum / world  # "ddp_mean": what DDP's averaging produces
+            torch.testing.assert_close(reduced, whole, rtol=1e-5, atol=1e-9)
+        with pytest.raises(ValueError):
+            global_mean(torch.zeros(()), grad_reduction="mean")
+        open(os.path.join(result_dir, f"ok{rank}"), "w").write("ok")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_loss_gradient_conventions(tmp_path):
+    """d(global loss)/d(local logits) must be SUMMED over ranks; under DDP's averaging use
+    grad_reduction="ddp_mean" (backward x world). Checked on parameter gradients against the whole-batch gradient."""
+    world = 2
+    mp.spawn(_grad_convention_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ok{r}")) for r in range(world))
