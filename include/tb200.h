@@ -337,6 +337,26 @@ TB_API int tb_lovasz_sorted(const float* err_sorted, const float* gt_sorted, con
                      int relu, float* seg_loss, float* grad_sorted, void* ws, size_t ws_bytes, void* stream);
 TB_API size_t tb_lovasz_workspace_bytes(int64_t total, int segs);
 
+/* Lovasz hinge (mode 0; BinaryLovaszLoss, lovasz.py:37-86,187-194) and Lovasz-softmax (mode 1; LovaszLoss with
+ * classes="present", lovasz.py:92-160,197-204) as ONE launch sequence for all (image, class) segments: errors + sort keys,
+ * segmented descending radix sort (4 x 8 bits, payload = ground-truth bit | sign | index), positives scan, Jaccard
+ * increments, dot product, means over present classes / images, and d loss / d input scattered back through the sorted
+ * permutation. No host loop, no host synchronisation, no library sort.
+ *   x       hinge: logits f32 [B,inner] (C must be 1); softmax: class PROBABILITIES f32 [B,C,inner] (no softmax is applied,
+ *           as in the reference; C == 1 means "sigmoid output": foreground = (label == 0), lovasz.py:129-132)
+ *   labels  [B,inner], TB_T_DENSE_F32 or TB_T_LABELS_I64; hinge labels must be 0/1 (or the ignore value)
+ *   per_image  one segment set per image and the mean over images (lovasz.py:45-49,101-105), else one over the batch
+ *   has_ignore / ignore  pixels whose label equals `ignore` are dropped (lovasz.py:82-86,156-160): they sort last and
+ *           get a zero gradient; an image / batch without valid pixels contributes 0
+ *   loss_out f32 [1]; grad f32, same shape as x, or NULL (= d loss_out / d x)
+ *   ws      tb_lovasz_fused_workspace_bytes(B, C, inner, per_image) bytes, 256-byte aligned (16 B per key + histograms)
+ * Limits: <= 2^30 elements per segment, <= 65535 segments. Ties between equal errors are ordered by pixel index (the loss
+ * is invariant to the order inside a tie group; torch.sort leaves it unspecified). */
+TB_API size_t tb_lovasz_fused_workspace_bytes(int64_t B, int C, int64_t inner, int per_image);
+TB_API int tb_lovasz_fwd_bwd(const float* x, const void* labels, int t_kind, int64_t B, int C, int64_t inner, int mode,
+                      int per_image, int has_ignore, float ignore, float* loss_out, float* grad, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Bench helper: the deterministic, D4-non-equivariant stand-in "model" of SURVEY.md section 8(d):
  *   y[b,k,i,j] = sum_c Wm[k,c]*x[b,c,i,j] + 0.01*(i - 2j + 7k)/T     (not part of the reference)

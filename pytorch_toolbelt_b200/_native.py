@@ -155,6 +155,8 @@ SIGNATURES = {
     "tb_scale_by_device_scalar": (_i, [_vp, _i64, _vp, _vp]),
     "tb_lovasz_sorted": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "tb_lovasz_workspace_bytes": (_sz, [_i64, _i]),
+    "tb_lovasz_fused_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),
+    "tb_lovasz_fwd_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "tb_standin_model": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -1,161 +1,106 @@
-"""Lovasz hinge / Lovasz-softmax: drop-in for ``pytorch_toolbelt/losses/lovasz.py`` (Berman et al. 2018).
+"""Lovasz hinge / Lovasz-softmax losses (Berman et al. 2018): drop-in for ``pytorch_toolbelt/losses/lovasz.py``.
 
-Sort-bound. The descending key sort is ``torch.sort`` (a library radix sort, like cuBLAS for a GEMM); everything
-after it -- positives count scan, Jaccard increments (lovasz.py:23-34), the dot product and the gradient w.r.t. the
-sorted errors -- is one fused CUDA pipeline (tb_lovasz_sorted), and the gradient is scattered back through the
-permutation. Counts are carried as exact integers (the reference's float32 cumsum loses integers above 2^24).
+The reference evaluates these with Python loops over images and classes, a boolean-mask gather for ignored pixels, one
+``torch.sort`` per (image, class) and float cumsums (lovasz.py:37-160). Here every (image, class) pair is a SEGMENT of one
+kernel sequence (``tb_lovasz_fwd_bwd``, csrc/lovasz.cu): error + sort-key construction, a hand-written segmented radix
+sort that carries the ground-truth bit and the pixel index as payload, the positives scan, the Jaccard increments, the
+dot product, the "present classes" / per-image means and the gradient scattered back through the permutation -- forward
+value and d loss / d input from one call, no host loop, no host synchronisation.
+
+Behaviour kept from the reference: ``LovaszLoss`` takes class PROBABILITIES and applies no softmax; ``BinaryLovaszLoss``
+takes logits; both run in float32 only (lovasz.py:29-31,71); a 3-D ``[B,H,W]`` input to ``LovaszLoss`` is the "sigmoid
+output" case with foreground = (label == 0) (lovasz.py:129-132,145-148); only classes present in the (valid) labels are
+averaged. Deviations, deliberate: positives are counted in exact integers (the reference's float32 cumsum stops counting
+at 2**24); an image / batch without a single valid pixel contributes 0 (the reference returns an empty tensor there).
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Union
 
 import torch
 from torch.nn.modules.loss import _Loss
 
 from .. import _native as N
+from .._native import TB
+from . import _kernels as K
 
-__all__ = ["BinaryLovaszLoss", "LovaszLoss"]
+__all__ = ["BinaryLovaszLoss", "LovaszLoss", "lovasz_hinge_loss", "lovasz_softmax_loss"]
+
+_HINGE, _SOFTMAX = 0, 1
 
 
-class _LovaszSortedDot(torch.autograd.Function):
-    """loss = dot(relu?(errors_sorted), lovasz_grad(gt_sorted)) for one flat segment."""
+class _LovaszFused(torch.autograd.Function):
+    """value + stored gradient from one tb_lovasz_fwd_bwd call; backward only scales by the upstream scalar."""
 
     @staticmethod
-    def forward(ctx, errors: torch.Tensor, fg: torch.Tensor, relu: bool):
+    def forward(ctx, scores: torch.Tensor, labels: torch.Tensor, mode: int, per_image: bool, ignore):
         N.require_cuda("Lovasz loss")
-        if errors.dtype != torch.float32:
-            raise TypeError("Lovasz losses run in float32 (like the reference, lovasz.py:29-31,71)")
-        err_sorted, perm = torch.sort(errors.detach(), dim=0, descending=True)
-        gt_sorted = fg.detach().to(torch.float32)[perm].contiguous()
-        n = err_sorted.numel()
-        device = errors.device
-        loss = torch.empty(1, dtype=torch.float32, device=device)
+        if scores.dtype != torch.float32:
+            raise TypeError(f"Lovasz losses run in float32 like the reference (lovasz.py:29-31,71), got {scores.dtype}")
+        origin = scores.device
+        x = scores.detach()
+        x = (x if x.is_cuda else x.cuda()).contiguous()
+        device = x.device
+        if mode == _HINGE:
+            if x.dim() >= 2 and labels.dim() == x.dim() - 1 and x.shape[1] == 1:
+                x = x.squeeze(1)  # [B,1,H,W] logits against [B,H,W] labels
+            batch, classes = (x.shape[0] if x.dim() >= 1 and x.numel() else 0), 1
+            inner = x.numel() // batch if batch else 0
+        else:
+            if x.dim() == 3:  # "sigmoid output": one probability plane (lovasz.py:145-148)
+                batch, classes = x.shape[0], 1
+            else:
+                batch, classes = x.shape[0], x.shape[1]
+            inner = x.numel() // (batch * classes) if batch * classes else 0
+        if labels.numel() != batch * inner:
+            raise ValueError(f"labels with {labels.numel()} elements do not match scores of shape {tuple(scores.shape)}")
+        y = labels.detach()
+        y = y if y.is_cuda else y.to(device)
+        if y.dtype == torch.float32:
+            t_kind = TB.T_DENSE_F32
+        else:
+            y, t_kind = y.to(torch.int64), TB.T_LABELS_I64
+        y = y.contiguous()
+        out = torch.zeros((), dtype=torch.float32, device=device)
         want_grad = ctx.needs_input_grad[0]
-        grad_sorted = torch.empty(n, dtype=torch.float32, device=device) if want_grad else None
-        ws = torch.empty(N.lib().tb_lovasz_workspace_bytes(n, 1), dtype=torch.uint8, device=device)
-        offsets = (C.c_int64 * 2)(0, n)
-        with torch.cuda.device(device):
-            rc = N.lib().tb_lovasz_sorted(err_sorted.data_ptr(), gt_sorted.data_ptr(), offsets, 1, int(relu), loss.data_ptr(),
-                                          N.ptr(grad_sorted), ws.data_ptr(), ws.numel(), N.stream_ptr(device))
-        N.check(rc, "tb_lovasz_sorted")
-        ctx.perm, ctx.grad_sorted, ctx.n = perm, grad_sorted, n
-        return loss[0]
+        grad = torch.empty_like(x) if want_grad else None
+        if batch * inner > 0:
+            lib = N.lib()
+            ws = torch.empty(lib.tb_lovasz_fused_workspace_bytes(batch, classes, inner, int(per_image)), dtype=torch.uint8,
+                             device=device)
+            with torch.cuda.device(device):
+                rc = lib.tb_lovasz_fwd_bwd(x.data_ptr(), y.data_ptr(), t_kind, batch, classes, inner, mode, int(per_image),
+                                           0 if ignore is None else 1, 0.0 if ignore is None else float(ignore),
+                                           out.data_ptr(), N.ptr(grad), ws.data_ptr(), ws.numel(), N.stream_ptr(device))
+            N.check(rc, "tb_lovasz_fwd_bwd")
+        elif grad is not None:
+            grad.zero_()
+        ctx.stored_grad, ctx.origin, ctx.x_shape = grad, origin, scores.shape
+        return out if origin.type == "cuda" else out.to(origin)
 
     @staticmethod
     def backward(ctx, upstream):
-        grad = torch.empty(ctx.n, dtype=torch.float32, device=ctx.grad_sorted.device)
-        grad[ctx.perm] = ctx.grad_sorted * upstream
-        return grad, None, None
+        grad = ctx.stored_grad
+        if grad is None:
+            raise RuntimeError("backward called twice on a fused loss; recompute the loss instead of retaining the graph")
+        ctx.stored_grad = None
+        grad = K.scale_stored_grad(grad, upstream).reshape(ctx.x_shape)
+        if ctx.origin.type != "cuda":
+            grad = grad.to(ctx.origin)
+        return grad, None, None, None, None
 
 
-def _lovasz_grad(gt_sorted):
-    """Gradient of the Lovasz extension w.r.t. sorted errors (Alg. 1 of the paper); host-visible helper kept for
-    API parity with the reference (lovasz.py:23-34); the losses below use the fused kernel instead."""
-    p = len(gt_sorted)
-    gts = gt_sorted.sum()
-    intersection = gts - gt_sorted.float().cumsum(0)
-    union = gts + (1 - gt_sorted).float().cumsum(0)
-    jaccard = 1.0 - intersection / union
-    if p > 1:
-        jaccard = torch.cat([jaccard[:1], jaccard[1:] - jaccard[:-1]])
-    return jaccard
+def lovasz_hinge_loss(logits: torch.Tensor, labels: torch.Tensor, per_image: bool = False,
+                      ignore_index: Optional[Union[int, float]] = None) -> torch.Tensor:
+    """Binary Lovasz hinge: ``logits`` [B,H,W] (or [B,1,H,W]), ``labels`` [B,H,W] in {0,1} (lovasz.py:37-86)."""
+    return _LovaszFused.apply(logits, labels, _HINGE, bool(per_image), ignore_index)
 
 
-def _mean(values, empty=0):
-    values = list(values)
-    if not values:
-        return empty
-    acc = values[0]
-    for v in values[1:]:
-        acc = acc + v
-    return acc if len(values) == 1 else acc / len(values)
-
-
-def _as_cuda(t: torch.Tensor) -> torch.Tensor:
-    N.require_cuda("Lovasz loss")
-    return t if t.is_cuda else t.cuda()
-
-
-def _lovasz_hinge_flat(logits, labels):
-    """logits [P] float, labels [P] {0,1} (lovasz.py:55-72)."""
-    if len(labels) == 0:
-        return logits.sum() * 0.0
-    signs = 2.0 * labels.float() - 1.0
-    errors = 1.0 - logits * signs
-    return _LovaszSortedDot.apply(errors, labels, True)
-
-
-def _flatten_binary_scores(scores, labels, ignore_index=None):
-    scores = scores.reshape(-1)
-    labels = labels.reshape(-1)
-    if ignore_index is None:
-        return scores, labels
-    valid = labels != ignore_index
-    return scores[valid], labels[valid]
-
-
-def _lovasz_hinge(logits, labels, per_image=True, ignore_index=None):
-    """Binary Lovasz hinge loss: logits [B,H,W], labels [B,H,W] in {0,1} (lovasz.py:37-52)."""
-    origin = logits.device
-    logits, labels = _as_cuda(logits), _as_cuda(labels)
-    if per_image:
-        loss = _mean(
-            _lovasz_hinge_flat(*_flatten_binary_scores(lg.unsqueeze(0), lb.unsqueeze(0), ignore_index))
-            for lg, lb in zip(logits, labels)
-        )
-    else:
-        loss = _lovasz_hinge_flat(*_flatten_binary_scores(logits, labels, ignore_index))
-    return loss if origin.type == "cuda" or not torch.is_tensor(loss) else loss.to(origin)
-
-
-def _lovasz_softmax_flat(probas, labels, classes="present"):
-    """probas [P,C], labels [P] (lovasz.py:112-140)."""
-    if probas.numel() == 0:
-        return probas * 0.0
-    num_classes = probas.size(1)
-    losses = []
-    class_to_sum = list(range(num_classes)) if classes in ["all", "present"] else classes
-    for c in class_to_sum:
-        fg = (labels == c).type_as(probas)
-        if classes == "present" and fg.sum() == 0:
-            continue
-        if num_classes == 1:
-            if len(classes) > 1:
-                raise ValueError("Sigmoid output possible only with 1 class")
-            class_pred = probas[:, 0]
-        else:
-            class_pred = probas[:, c]
-        errors = (fg - class_pred).abs()
-        losses.append(_LovaszSortedDot.apply(errors, fg, False))
-    return _mean(losses)
-
-
-def _flatten_probas(probas, labels, ignore=None):
-    if probas.dim() == 3:
-        probas = probas.unsqueeze(1)
-    num_classes = probas.size(1)
-    probas = torch.movedim(probas, 1, -1).contiguous().view(-1, num_classes)
-    labels = labels.reshape(-1)
-    if ignore is None:
-        return probas, labels
-    valid = labels != ignore
-    return probas[valid], labels[valid]
-
-
-def _lovasz_softmax(probas, labels, classes="present", per_image=False, ignore_index=None):
-    """Multi-class Lovasz-Softmax: probas [B,C,H,W] class PROBABILITIES (no softmax is applied, as upstream),
-    labels [B,H,W] (lovasz.py:92-109)."""
-    origin = probas.device
-    probas, labels = _as_cuda(probas), _as_cuda(labels)
-    if per_image:
-        loss = _mean(
-            _lovasz_softmax_flat(*_flatten_probas(prob.unsqueeze(0), lab.unsqueeze(0), ignore_index), classes=classes)
-            for prob, lab in zip(probas, labels)
-        )
-    else:
-        loss = _lovasz_softmax_flat(*_flatten_probas(probas, labels, ignore_index), classes=classes)
-    return loss if origin.type == "cuda" or not torch.is_tensor(loss) else loss.to(origin)
+def lovasz_softmax_loss(probas: torch.Tensor, labels: torch.Tensor, per_image: bool = False,
+                        ignore_index: Optional[Union[int, float]] = None) -> torch.Tensor:
+    """Multi-class Lovasz-softmax over the classes present in ``labels``: ``probas`` [B,C,H,W] class probabilities (or
+    [B,H,W] for a single sigmoid output), ``labels`` [B,H,W] (lovasz.py:92-160)."""
+    return _LovaszFused.apply(probas, labels, _SOFTMAX, bool(per_image), ignore_index)
 
 
 class BinaryLovaszLoss(_Loss):
@@ -165,7 +110,7 @@ class BinaryLovaszLoss(_Loss):
         self.per_image = per_image
 
     def forward(self, logits, target):
-        return _lovasz_hinge(logits, target, per_image=self.per_image, ignore_index=self.ignore_index)
+        return lovasz_hinge_loss(logits, target, per_image=self.per_image, ignore_index=self.ignore_index)
 
 
 class LovaszLoss(_Loss):
@@ -175,4 +120,4 @@ class LovaszLoss(_Loss):
         self.per_image = per_image
 
     def forward(self, logits, target):
-        return _lovasz_softmax(logits, target, per_image=self.per_image, ignore_index=self.ignore)
+        return lovasz_softmax_loss(logits, target, per_image=self.per_image, ignore_index=self.ignore)

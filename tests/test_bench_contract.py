@@ -29,7 +29,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["unit"] == "MP/s" and "megapixels/sec" in d["metric"]
     assert str(baseline.get("metric", "")).split()[0].lower() in d["metric"].lower() or "megapixel" in d["metric"].lower()
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "cfg2" in d["config"]["workload"]

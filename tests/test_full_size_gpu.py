@@ -98,9 +98,19 @@ def test_cfg1_full_size_against_the_oracle_and_the_reference_test():
     for s in range(0, len(tiles), 8):
         batch = torch.stack(tiles[s : s + 8]).float().cuda()
         merger.integrate_batch(batch.max(dim=1, keepdim=True)[0], tiler.crops[s : s + 8])
-    merged = np.moveaxis(to_numpy(merger.merge()), 0, -1).astype(np.uint8)
-    merged = tiler.crop_to_orignal_size(merged)
+    # the reference test casts with .astype(np.uint8) (its image is all zeros: np.random.random(...).astype(uint8)); with real
+    # pixel values a weighted mean of equal numbers can land at 192.99999, so round instead of truncating
+    merged_f = np.moveaxis(to_numpy(merger.merge()), 0, -1)
+    merged = tiler.crop_to_orignal_size(np.rint(merged_f).astype(np.uint8))
     np.testing.assert_equal(merged, image.max(axis=2, keepdims=True))
+    np.testing.assert_allclose(tiler.crop_to_orignal_size(merged_f), image.max(axis=2, keepdims=True).astype(np.float32), atol=1e-3)
+    zero = np.random.random((2048, 2048, 3)).astype(np.uint8)  # exactly the reference's input
+    merger0 = CudaTileMerger(tiler.target_shape, 1, tiler.weight)
+    tiles0 = [tensor_from_rgb_image(tile) for tile in tiler.split(zero)]
+    for s in range(0, len(tiles0), 8):
+        merger0.integrate_batch(torch.stack(tiles0[s : s + 8]).float().cuda().max(dim=1, keepdim=True)[0], tiler.crops[s : s + 8])
+    np.testing.assert_equal(tiler.crop_to_orignal_size(np.moveaxis(to_numpy(merger0.merge()), 0, -1).astype(np.uint8)),
+                            zero.max(axis=2, keepdims=True))
 
 
 def test_cfg4_geometry_crop_against_the_oracle():
