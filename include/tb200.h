@@ -239,6 +239,37 @@ TB_API int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batch
                                 int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
                                 int raw, int top, int left, int H, int W, float* out_num, float* out_den, void* stream);
 
+/* Options on top of tb_merge_all / tb_merge_all_batched; NULL = none of them.
+ *   pre / temperature   activation applied to every prediction BEFORE the view reduction, as the reference's
+ *                       ApplySigmoidTo(model, temperature) wrapper does in front of the TTA mean
+ *                       (inference/ensembling.py:46-68: output.mul(temperature).sigmoid_())
+ *   out_mode            what the epilogue writes (raw == 0 only):
+ *                         TB_OUT_LOGITS  f32 [K,H,W] into out_num (the default)
+ *                         TB_OUT_ARGMAX  u8 [H,W] into out_u8 = merged.argmax(dim=0) (first maximum wins, NaN maximal; K <= 256)
+ *                         TB_OUT_MASK    u8 [K,H,W] into out_u8 = merged.sigmoid() > threshold
+ *                       replaces `merged.argmax(0).byte()` / `(merged.sigmoid() > thr).byte()` after TileMerger.merge
+ *                       (README.md:225, utils/torch_utils.py:144-159): no float canvas is written at all and one byte per
+ *                       pixel leaves the GPU; out_num may be NULL in these modes. */
+enum tb_pre_activation { TB_PRE_NONE = 0, TB_PRE_SIGMOID = 1 };
+enum tb_out_mode { TB_OUT_LOGITS = 0, TB_OUT_ARGMAX = 1, TB_OUT_MASK = 2 };
+typedef struct tb_merge_extra {
+  int pre;
+  float temperature;
+  int out_mode;
+  float threshold;
+  uint8_t* out_u8;
+} tb_merge_extra;
+
+TB_API int tb_merge_all_ex(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                    int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
+                    int raw, int top, int left, int H, int W, float* out_num, float* out_den, const tb_merge_extra* ex,
+                    void* stream);
+TB_API int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
+                                   int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                                   int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
+                                   int raw, int top, int left, int H, int W, float* out_num, float* out_den,
+                                   const tb_merge_extra* ex, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LOSSES  (forward value + gradient w.r.t. the logits in one call)
  * Layout for all of them: x is [B,C,inner] contiguous (inner = product of spatial dims).

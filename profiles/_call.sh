@@ -1,8 +1,10 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out/r2
-python profiles/calib_bw.py > gpurun_out/r2/calib_bw.json 2>&1; cat gpurun_out/r2/calib_bw.json
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/r2/gpu_tests_b.log 2>&1; echo "tests rc=$?"
-tail -25 gpurun_out/r2/gpu_tests_b.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'merge_all' --launch-skip 3 -c 2 -o gpurun_out/r2/prof_cfg5_merge -f python profiles/bench_configs.py cfg5_table_weight > gpurun_out/r2/ncu_cfg5m.log 2>&1; echo "ncu rc=$?"
-tail -5 gpurun_out/r2/ncu_cfg5m.log
+timeout 900 python -m pytest tests/test_lovasz_gpu.py tests/test_losses_gpu.py -q --timeout 600 > gpurun_out/r2/lovasz_tests.log 2>&1; echo "lovasz rc=$?"
+tail -40 gpurun_out/r2/lovasz_tests.log
+timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_lovasz_gpu.py -q --timeout 800 -k "variants or ties or argument" > gpurun_out/r2/lovasz_memcheck.log 2>&1; echo "memcheck rc=$?"
+tail -8 gpurun_out/r2/lovasz_memcheck.log
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --deselect tests/test_lovasz_gpu.py --deselect tests/test_losses_gpu.py > gpurun_out/r2/gpu_tests_c.log 2>&1; echo "tests rc=$?"
+tail -25 gpurun_out/r2/gpu_tests_c.log
+TB200_FORCE_GENERIC_MERGE=1 python profiles/bench_configs.py cfg5_table_weight cfg5 cfg1 > gpurun_out/r2/cfg5_generic.json 2>&1; cat gpurun_out/r2/cfg5_generic.json

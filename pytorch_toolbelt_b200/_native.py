@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-__all__ = ["lib", "check", "TB", "stream_ptr", "require_cuda", "Weight", "Grid", "FocalParams", "DiceParams"]
+__all__ = ["lib", "check", "TB", "stream_ptr", "require_cuda", "Weight", "Grid", "MergeExtra", "FocalParams", "DiceParams"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libtb200.so")
@@ -30,6 +30,8 @@ class TB:
     RED_NONE, RED_MEAN, RED_SUM, RED_GMEAN, RED_HMEAN, RED_HARMONIC1P, RED_LOGODD, RED_LOG1P = range(8)
     W_TABLE, W_ONES, W_PYRAMID, W_GAUSSIAN = range(4)
     LOSS_NONE, LOSS_MEAN, LOSS_SUM, LOSS_BATCHWISE = range(4)
+    PRE_NONE, PRE_SIGMOID = 0, 1
+    OUT_LOGITS, OUT_ARGMAX, OUT_MASK = 0, 1, 2
     T_DENSE_F32, T_LABELS_I64 = 0, 1
     # view code bits (tb_view_permute)
     V_T, V_FI, V_FJ = 1, 2, 4
@@ -85,6 +87,13 @@ class Grid(C.Structure):
     ]
 
 
+class MergeExtra(C.Structure):
+    """tb_merge_extra (include/tb200.h): pre-activation before the view reduction, label / mask output modes."""
+
+    _fields_ = [("pre", C.c_int), ("temperature", C.c_float), ("out_mode", C.c_int), ("threshold", C.c_float),
+                ("out_u8", C.c_void_p)]
+
+
 class FocalParams(C.Structure):
     _fields_ = [
         ("gamma", C.c_float),
@@ -137,6 +146,16 @@ SIGNATURES = {
         _i,
         [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
          _i, _i, _vp, _vp, _vp],
+    ),
+    "tb_merge_all_ex": (
+        _i,
+        [_vp, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i,
+         _vp, _vp, C.POINTER(MergeExtra), _vp],
+    ),
+    "tb_merge_all_batched_ex": (
+        _i,
+        [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
+         _i, _i, _vp, _vp, C.POINTER(MergeExtra), _vp],
     ),
     "tb_loss_workspace_bytes": (_sz, [_i64, _i, _i64]),
     "tb_focal_fwd_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(FocalParams), _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "merge_tma.cuh"
+#include "tiles_args.cuh"
 
 namespace tb {
 
@@ -167,18 +168,7 @@ __device__ __forceinline__ void emit_views(const T* sm, int R0, int C0, int vr, 
 // ------------------------------------------------------------------------------------------------
 // 2. slice + HWC->CHW + cast + TTA augment
 // ------------------------------------------------------------------------------------------------
-struct SliceArgs {
-  const void* img;
-  float* out;
-  const int32_t* xy;
-  int layout, H, W, C, n, Th, Tw, border;
-  int nbx, nby;  // blocks per tile
-  ViewSet views;
-  float bval[4];
-  int has_affine;
-  float scale[8], bias[8];  // first 8 channels by value; more channels -> identity (host rejects)
-};
-
+// SliceArgs: tiles_args.cuh
 __device__ __forceinline__ float to_f32(unsigned char v) { return (float)v; }
 __device__ __forceinline__ float to_f32(unsigned short v) { return (float)v; }
 __device__ __forceinline__ float to_f32(short v) { return (float)v; }
@@ -358,9 +348,16 @@ TB_VIEWS(TB_TTA_D4, 8, V_ID, V_T | V_FI, V_FI | V_FJ, V_T | V_FJ, V_T, V_FJ, V_T
 //   (Hs, Ws)     plane dims (identical for all views: transposing views require square planes)
 //   sm           CTA-shared staging: [nT][BS][PITCH], nT = number of transposing views (<= 4)
 // Contains two __syncthreads() when the view set has transposing views: call it from uniform control flow.
+template <typename T>
+__device__ __forceinline__ T pre_act_t(int pre, float temperature, T v) {
+  if (pre == TB_PRE_SIGMOID) return T(1) / (T(1) + exp(-(v * T(temperature))));
+  return v;
+}
+
 template <typename T, bool ALIGNED, unsigned PACKED, int COUNT>
 __device__ __forceinline__ void deaug_reduce4(const T* __restrict__ plane0, size_t view_stride, int red, int i0,
-                                              int j0, int Hs, int Ws, T* sm, T out[4]) {
+                                              int j0, int Hs, int Ws, T* sm, T out[4], int pre = TB_PRE_NONE,
+                                              float temperature = 1.f) {
   constexpr bool HAS_T = packed_has_transpose(PACKED, COUNT);
   const int li = threadIdx.x >> 3, lq = threadIdx.x & 7;
   const int i = i0 + li, j = j0 + 4 * lq;
@@ -412,7 +409,7 @@ __device__ __forceinline__ void deaug_reduce4(const T* __restrict__ plane0, size
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const T pv = red_pre<T>(red, v[e]);
+        const T pv = red_pre<T>(red, pre_act_t<T>(pre, temperature, v[e]));
         acc[e] = (a == 0) ? pv : add_rn(acc[e], pv);  // sequential view-order sum (torch CPU mean/sum)
       }
     }
@@ -846,21 +843,7 @@ __global__ void __launch_bounds__(kThreads) logits_to_labels_kernel(const float*
 // ------------------------------------------------------------------------------------------------
 // 7. output-stationary fused de-augment + merge + normalise + crop
 // ------------------------------------------------------------------------------------------------
-struct MergeAllArgs {
-  const float* pred;
-  tb_grid grid;
-  int K, red, Hp, Wp, y0, y1, r0, r1, raw, top, left, H, W;
-  int bx0, nbx, nby;  // block-column offset and block counts covering the requested window
-  int debug;          // TB200_TMA_DEBUG bits (diagnostics only)
-  // TMA path: tile t (grid order) lives in batch tensor (t - first_tile) / batch_tiles at position (t - first_tile) % batch_tiles
-  int first_tile, batch_tiles, covered_tiles;
-  ViewSet views;
-  WeightDev<float> w;
-  const float* init_num;
-  const float* init_den;
-  float* out_num;
-  float* out_den;
-};
+// MergeAllArgs: tiles_args.cuh
 
 template <bool ALIGNED, int TTA>
 __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
@@ -887,6 +870,7 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
   int cb = min((X0 + BS - 1) / g.Sx, g.nx - 1);
 
   const bool y_ok = (y >= a.y0 && y < a.y1);
+  LabelState ls;
   for (int k = 0; k < a.K; ++k) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
     if (a.init_num && y_ok) {
@@ -940,7 +924,7 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
           if (ok[u]) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float val = red_post<float>(a.red, red_pre<float>(a.red, pv[u][e]), 1);
+              const float val = red_post<float>(a.red, red_pre<float>(a.red, pre_act(a.pre, a.temperature, pv[u][e])), 1);
               acc[e] = add_rn(acc[e], mul_rn(val, wv[u][e]));
               den[e] = add_rn(den[e], wv[u][e]);
             }
@@ -965,7 +949,7 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
         const int i0 = Y0 - r * g.Sy, j0 = X0 - c * g.Sx;
         float v[4];
         deaug_reduce4<float, ALIGNED, V::packed, V::count>(base + (size_t)k * plane, vstride, a.red, i0, j0, g.Th,
-                                                           g.Tw, sm, v);
+                                                           g.Tw, sm, v, a.pre, a.temperature);
         const int i = i0 + li, j = j0 + 4 * lq;
         if (i >= 0 && i < g.Th) {
 #pragma unroll
@@ -989,21 +973,10 @@ __global__ void __launch_bounds__(kThreads) merge_all_kernel(MergeAllArgs a) {
           if (k == 0) a.out_den[o + e] = den[e];
         }
     } else {
-      const int oi = y - a.top;
-      if (oi >= 0 && oi < a.H) {
-        float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
-        const int oj = x - a.left;
-        if (ALIGNED && ((a.left & 3) == 0) && ((a.W & 3) == 0) && oj >= 0 && oj + 3 < a.W) {
-          float q[4];
+      float q[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) q[e] = acc[e] / den[e];
-          __stcs(reinterpret_cast<float4*>(o + oj), make_float4(q[0], q[1], q[2], q[3]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (oj + e >= 0 && oj + e < a.W) o[oj + e] = acc[e] / den[e];
-        }
-      }
+      for (int e = 0; e < 4; ++e) q[e] = acc[e] / den[e];
+      merge_epilogue(a, k, y - a.top, x - a.left, q, ls);
     }
   }
 }
@@ -1043,7 +1016,7 @@ struct TmaOffsets {
   }
   // sequential view-order sum of the (transformed) view values of this thread's 4 pixels
   template <bool LINEAR>
-  __device__ __forceinline__ void reduce(const float* st, int red, float v[4]) const {
+  __device__ __forceinline__ void reduce(const float* st, int red, float v[4], int pre = TB_PRE_NONE, float temperature = 1.f) const {
 #pragma unroll
     for (int va = 0; va < NV; ++va) {
       const unsigned gc = view_inverse((PACKED >> (3 * va)) & 7u);
@@ -1061,7 +1034,7 @@ struct TmaOffsets {
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = LINEAR ? q[e] : red_pre<float>(red, q[e]);
+        const float pv = LINEAR ? q[e] : red_pre<float>(red, pre_act(pre, temperature, q[e]));
         v[e] = (va == 0) ? pv : add_rn(v[e], pv);
       }
     }
@@ -1252,6 +1225,7 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
   offs.init(li, cq);
 
   int it = 0;
+  LabelState ls;
   for (int blk = blk0; blk < nblocks; blk += blk_step) {
     const BlockWork w = block_work(a, blk);
     const int nt = block_tile_count(a, w);
@@ -1296,7 +1270,7 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
         for (int gi = 0; gi < G; ++gi) {
           if (gi < cnt) {
             float v[4];
-            offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v);
+            offs.template reduce<LINEAR>(boxes + ((size_t)s * SB + gi * NV) * kBoxFloats, a.red, v, a.pre, a.temperature);
             if (gi == cnt - 1)  // slot back to the producer (debug bit 16: timing-only switch that drops the proxy fence)
               mbar_release_after(&empty[s], v[0], v[1], v[2], v[3], lane == 0, (a.debug & 16) != 0);
 #pragma unroll
@@ -1314,19 +1288,8 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
         *reinterpret_cast<float4*>(a.out_num + (size_t)k * rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (k == 0) *reinterpret_cast<float4*>(a.out_den + o) = make_float4(den[0], den[1], den[2], den[3]);
       } else {
-        const int oi = y - a.top;
-        if (oi >= 0 && oi < a.H) {
-          float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
-          const int oj = w.X0 + lj - a.left;
-          if (((a.left & 3) == 0) && ((a.W & 3) == 0) && oj >= 0 && oj + 3 < a.W) {
-            __stcs(reinterpret_cast<float4*>(o + oj),
-                   make_float4(acc[0] / den[0], acc[1] / den[1], acc[2] / den[2], acc[3] / den[3]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (oj + e >= 0 && oj + e < a.W) o[oj + e] = acc[e] / den[e];
-          }
-        }
+        const float q[4] = {acc[0] / den[0], acc[1] / den[1], acc[2] / den[2], acc[3] / den[3]};
+        merge_epilogue(a, k, y - a.top, w.X0 + lj - a.left, q, ls);
       }
     }
   }
@@ -1510,6 +1473,12 @@ static inline int merge_variant() {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// TB200_SINGLE_VIEW=0 keeps TTA_NONE on the general kernels (A/B switch; tests cross-check the two bit for bit)
+static inline bool single_view_enabled() {
+  const char* v = getenv("TB200_SINGLE_VIEW");
+  return !(v && v[0] == '0');
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -1558,7 +1527,6 @@ static bool make_pred_tensor_map(const float* base, int b, int K, int Th, int Tw
   return r == CUDA_SUCCESS;
 }
 
-constexpr int kMaxTmaBatches = 192;  // 192 x 128 B of tensor maps = 24 KB of kernel parameters (limit 32 KB)
 
 template <int TTA, bool LINEAR, int MAXB, int NG>
 static cudaError_t launch_merge_all_tma_impl2(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
@@ -1588,7 +1556,7 @@ static cudaError_t launch_merge_all_tma_impl(const MergeAllArgs& a, const TmaMap
 
 template <int TTA, int MAXB>
 static cudaError_t launch_merge_all_tma(const MergeAllArgs& a, const TmaMaps<MAXB>& maps, int nblocks, cudaStream_t s) {
-  if (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) return launch_merge_all_tma_impl<TTA, true, MAXB>(a, maps, nblocks, s);
+  if ((a.red == TB_RED_MEAN || a.red == TB_RED_SUM) && a.pre == TB_PRE_NONE) return launch_merge_all_tma_impl<TTA, true, MAXB>(a, maps, nblocks, s);
   return launch_merge_all_tma_impl<TTA, false, MAXB>(a, maps, nblocks, s);
 }
 
@@ -1690,7 +1658,9 @@ int tb_slice_augment(const void* img, int img_dtype, int layout, int H, int W, i
   cudaStream_t s = (cudaStream_t)stream;
 #define TB_SLICE(SrcT)                                                                   \
   do {                                                                                   \
-    if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out) && n <= 65535) {           \
+    if (tta == TB_TTA_NONE && single_view_enabled() &&                                   \
+        launch_slice_single_view(a, img_dtype, s) != cudaErrorNotSupported) {            \
+    } else if (tta == TB_TTA_NONE && (Tw % 4 == 0) && aligned16(out) && n <= 65535) {    \
       const int bands = std::max(1, std::min(Th / 8, std::max(1, (sm_count() * 8 + n - 1) / n))); \
       dim3 g((unsigned)bands, (unsigned)n);                                              \
       slice_plain_kernel<SrcT><<<g, kThreads, 0, s>>>(a);                                \
@@ -1962,10 +1932,48 @@ int tb_logits_to_labels(const float* logits, int K, int64_t plane_stride, int64_
   return TB_OK;
 }
 
+}  // extern "C"
+
+// pre-activation / output-mode options shared by tb_merge_all_ex and tb_merge_all_batched_ex
+static int apply_merge_extra(const tb_merge_extra* ex, int raw, int K, float*& out_num, MergeAllArgs* a) {
+  a->pre = TB_PRE_NONE; a->temperature = 1.f; a->out_mode = TB_OUT_LOGITS; a->thr = 0.5f; a->out_u8 = nullptr;
+  if (ex) {
+    TB_REQUIRE(ex->pre == TB_PRE_NONE || ex->pre == TB_PRE_SIGMOID, TB_ERR_ARG, "tb_merge_all: bad pre-activation %d", ex->pre);
+    TB_REQUIRE(ex->out_mode >= TB_OUT_LOGITS && ex->out_mode <= TB_OUT_MASK, TB_ERR_ARG, "tb_merge_all: bad out_mode %d", ex->out_mode);
+    a->pre = ex->pre; a->temperature = ex->temperature; a->out_mode = ex->out_mode; a->thr = ex->threshold; a->out_u8 = ex->out_u8;
+    if (ex->out_mode != TB_OUT_LOGITS) {
+      TB_REQUIRE(!raw, TB_ERR_ARG, "tb_merge_all: label / mask output needs the normalised (raw = 0) mode");
+      TB_REQUIRE(ex->out_u8, TB_ERR_ARG, "tb_merge_all: out_mode %d needs out_u8", ex->out_mode);
+      TB_REQUIRE(ex->out_mode != TB_OUT_ARGMAX || K <= 256, TB_ERR_UNSUPPORTED, "tb_merge_all: argmax into uint8 needs K <= 256");
+    }
+  }
+  a->out_num = out_num;
+  a->vec_ok = aligned16(out_num) && (!a->out_u8 || (reinterpret_cast<uintptr_t>(a->out_u8) & 3) == 0);
+  return TB_OK;
+}
+
+extern "C" {
+
 int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
                  int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw,
                  int top, int left, int H, int W, float* out_num, float* out_den, void* stream) {
-  TB_REQUIRE(grid && weight && out_num, TB_ERR_ARG, "tb_merge_all: null pointer");
+  return tb_merge_all_ex(pred, grid, K, tta, reduction, weight, Hp, Wp, y0, y1, r0, r1, init_num, init_den, raw, top, left, H, W,
+                         out_num, out_den, nullptr, stream);
+}
+
+int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
+                         int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight, int Hp,
+                         int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw, int top,
+                         int left, int H, int W, float* out_num, float* out_den, void* stream) {
+  return tb_merge_all_batched_ex(batch_ptrs_host, n_batches, batch_tiles, last_batch_tiles, first_tile, grid, K, tta, reduction,
+                                 weight, Hp, Wp, y0, y1, r0, r1, init_num, init_den, raw, top, left, H, W, out_num, out_den, nullptr,
+                                 stream);
+}
+
+int tb_merge_all_ex(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
+                    int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw,
+                    int top, int left, int H, int W, float* out_num, float* out_den, const tb_merge_extra* ex, void* stream) {
+  TB_REQUIRE(grid && weight && (out_num || (ex && ex->out_mode != TB_OUT_LOGITS)), TB_ERR_ARG, "tb_merge_all: null pointer");
   TB_REQUIRE(pred || grid->tile_ptr, TB_ERR_ARG, "tb_merge_all: need pred or grid->tile_ptr");
   TB_REQUIRE(!grid->tile_ptr || grid->tile_vstride, TB_ERR_ARG, "tb_merge_all: tile_ptr needs tile_vstride");
   TB_REQUIRE(K > 0 && grid->nx > 0 && grid->ny > 0 && grid->Sx > 0 && grid->Sy > 0 && grid->Th > 0 && grid->Tw > 0 &&
@@ -1987,7 +1995,11 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   TB_REQUIRE(make_weight<float>(weight, grid->Th, grid->Tw, &a.w), TB_ERR_ARG, "tb_merge_all: bad weight spec");
   a.pred = pred; a.grid = *grid; a.K = K; a.red = reduction; a.Hp = Hp; a.Wp = Wp;
   a.y0 = y0; a.y1 = y1; a.r0 = r0; a.r1 = r1; a.raw = raw; a.top = top; a.left = left; a.H = H; a.W = W;
-  a.init_num = init_num; a.init_den = init_den; a.out_num = out_num; a.out_den = out_den;
+  a.init_num = init_num; a.init_den = init_den; a.out_den = out_den;
+  {
+    const int rc = apply_merge_extra(ex, raw, K, out_num, &a);
+    if (rc != TB_OK) return rc;
+  }
   {
     const char* dbg = getenv("TB200_TMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
@@ -2001,13 +2013,25 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   const long long blocks = (long long)a.nbx * a.nby;
   TB_REQUIRE(blocks > 0 && blocks < (1ll << 31), TB_ERR_ARG, "tb_merge_all: grid too large");
   const bool al = (grid->Th % 4 == 0) && (grid->Tw % 4 == 0) && (grid->Sx % 4 == 0) && (grid->Sy % 4 == 0) &&
-                  (!pred || aligned16(pred)) && !grid->tile_ptr && aligned16(out_num) &&
+                  (!pred || aligned16(pred)) && !grid->tile_ptr && a.vec_ok &&
                   (weight->kind != TB_W_TABLE || aligned16(weight->table));
   // with a pointer table the caller vouches for 16-byte aligned planes via tile_vstride % 4 == 0 (checked by the shim)
   const bool al_tbl = grid->tile_ptr && (grid->Th % 4 == 0) && (grid->Tw % 4 == 0) && (grid->Sx % 4 == 0) &&
-                      (grid->Sy % 4 == 0) && aligned16(out_num) &&
+                      (grid->Sy % 4 == 0) && a.vec_ok &&
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
+  // single view (no TTA): plain-load kernel, no staging (single_view.cu)
+  if (a.views.count == 1 && al && pred && !grid->tile_slot && single_view_enabled() && !tb_force_generic_merge()) {
+    a.first_tile = 0;
+    a.batch_tiles = grid->n_slots;
+    a.covered_tiles = grid->n_slots;
+    BatchPtrs ptrs;
+    ptrs.p[0] = pred;
+    const cudaError_t e = launch_merge_single_view(a, ptrs, s);
+    if (e == cudaSuccess) return TB_OK;
+    if (e != cudaErrorNotSupported) return cuda_fail(e, "merge_single_view_kernel");
+    (void)cudaGetLastError();
+  }
   // TMA-pipelined path: one pred tensor, tile geometry on the 32-pixel block lattice
   if (al && pred && !grid->tile_slot && tma_geometry_ok(grid, Wp, init_num, init_den, raw, out_num, out_den, weight)) {
     TmaMaps<1> maps;
@@ -2030,11 +2054,12 @@ int tb_merge_all(const float* pred, const tb_grid* grid, int K, int tta, int red
   return TB_OK;
 }
 
-int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
-                         int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight, int Hp,
-                         int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw, int top,
-                         int left, int H, int W, float* out_num, float* out_den, void* stream) {
-  TB_REQUIRE(batch_ptrs_host && grid && weight && out_num, TB_ERR_ARG, "tb_merge_all_batched: null pointer");
+int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_batches, int batch_tiles, int last_batch_tiles,
+                            int first_tile, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight, int Hp,
+                            int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den, int raw, int top,
+                            int left, int H, int W, float* out_num, float* out_den, const tb_merge_extra* ex, void* stream) {
+  TB_REQUIRE(batch_ptrs_host && grid && weight && (out_num || (ex && ex->out_mode != TB_OUT_LOGITS)), TB_ERR_ARG,
+             "tb_merge_all_batched: null pointer");
   TB_REQUIRE(n_batches > 0 && batch_tiles > 0 && last_batch_tiles > 0 && last_batch_tiles <= batch_tiles && first_tile >= 0,
              TB_ERR_ARG, "tb_merge_all_batched: bad batch description");
   TB_REQUIRE(K > 0 && grid->nx > 0 && grid->ny > 0 && grid->Sx > 0 && grid->Sy > 0 && grid->Th > 0 && grid->Tw > 0,
@@ -2063,7 +2088,11 @@ int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int
   a.pred = nullptr; a.grid = *grid; a.K = K; a.red = reduction; a.Hp = Hp; a.Wp = Wp;
   a.grid.tile_slot = nullptr; a.grid.tile_ptr = nullptr; a.grid.tile_vstride = nullptr;
   a.y0 = y0; a.y1 = y1; a.r0 = r0; a.r1 = r1; a.raw = raw; a.top = top; a.left = left; a.H = H; a.W = W;
-  a.init_num = init_num; a.init_den = init_den; a.out_num = out_num; a.out_den = out_den;
+  a.init_num = init_num; a.init_den = init_den; a.out_den = out_den;
+  {
+    const int rc = apply_merge_extra(ex, raw, K, out_num, &a);
+    if (rc != TB_OK) return rc;
+  }
   {
     const char* dbg = getenv("TB200_TMA_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
@@ -2078,6 +2107,18 @@ int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batches, int
   TB_REQUIRE(blocks > 0 && blocks < (1ll << 31), TB_ERR_ARG, "tb_merge_all_batched: grid too large");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaErrorInvalidValue;
+  if (a.views.count == 1 && single_view_enabled()) {
+    BatchPtrs ptrs;
+    for (int i = 0; i < n_batches; ++i) ptrs.p[i] = batch_ptrs_host[i];
+    const int keep = a.batch_tiles;
+    if (n_batches == 1) a.batch_tiles = last_batch_tiles;
+    e = launch_merge_single_view(a, ptrs, s);
+    if (e == cudaSuccess) return TB_OK;
+    if (e != cudaErrorNotSupported) return cuda_fail(e, "merge_single_view_kernel(batched)");
+    (void)cudaGetLastError();
+    a.batch_tiles = keep;
+    e = cudaErrorInvalidValue;
+  }
   if (n_batches == 1) {
     TmaMaps<1> maps;
     if (!make_pred_tensor_map(batch_ptrs_host[0], last_batch_tiles, K, grid->Th, grid->Tw, a.views.count, &maps.m[0]))

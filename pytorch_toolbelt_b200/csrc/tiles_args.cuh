@@ -1,0 +1,121 @@
+// Argument blocks shared by the tile kernels' translation units (tiles.cu, single_view.cu) and the launchers that
+// one unit exposes to the other. Device code only; the C-ABI structs (tb_grid, tb_weight) come from include/tb200.h.
+#pragma once
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kMaxTmaBatches = 192;  // 192 x 128 B of tensor maps = 24 KB of kernel parameters (limit 32 KB)
+
+struct SliceArgs {
+  const void* img;
+  float* out;
+  const int32_t* xy;
+  int layout, H, W, C, n, Th, Tw, border;
+  int nbx, nby;  // blocks per tile
+  ViewSet views;
+  float bval[4];
+  int has_affine;
+  float scale[8], bias[8];  // first 8 channels by value; more channels -> identity (host rejects)
+};
+
+
+struct MergeAllArgs {
+  const float* pred;
+  tb_grid grid;
+  int K, red, Hp, Wp, y0, y1, r0, r1, raw, top, left, H, W;
+  int bx0, nbx, nby;  // block-column offset and block counts covering the requested window
+  int debug;          // TB200_TMA_DEBUG bits (diagnostics only)
+  // TMA path: tile t (grid order) lives in batch tensor (t - first_tile) / batch_tiles at position (t - first_tile) % batch_tiles
+  int first_tile, batch_tiles, covered_tiles;
+  ViewSet views;
+  WeightDev<float> w;
+  const float* init_num;
+  const float* init_den;
+  float* out_num;
+  float* out_den;
+  // activation applied to every prediction BEFORE the view reduction (ApplySigmoidTo, ensembling.py:46-68)
+  int pre;            // TB_PRE_NONE | TB_PRE_SIGMOID
+  float temperature;  // logits are multiplied by this first
+  // what the epilogue writes instead of float logits (normalised, cropped output only)
+  int out_mode;       // TB_OUT_LOGITS | TB_OUT_ARGMAX (u8 [H,W]) | TB_OUT_MASK (u8 [K,H,W], sigmoid(logit) > thr)
+  float thr;
+  unsigned char* out_u8;
+  int vec_ok;         // out_num 16-byte / out_u8 4-byte aligned: vector stores allowed
+};
+
+__device__ __forceinline__ float pre_act(int pre, float T, float v) {
+  if (pre == TB_PRE_SIGMOID) return 1.f / (1.f + expf(-(v * T)));  // x.mul(T).sigmoid_()
+  return v;
+}
+
+// Epilogue of the output-stationary merges for the 4 consecutive pixels (row oi, columns oj..oj+3 of the CROPPED output) a
+// thread owns; called once per channel k, k ascending, by the same thread for the same pixels, so an argmax over channels
+// is a running maximum in registers (first maximum wins, NaN is maximal: torch.argmax).
+struct LabelState {
+  float best[4];
+  int arg[4];
+};
+
+__device__ __forceinline__ void merge_epilogue(const MergeAllArgs& a, int k, int oi, int oj, const float q[4], LabelState& ls) {
+  if (oi < 0 || oi >= a.H) return;
+  const bool vec = a.vec_ok && ((a.left & 3) == 0) && ((a.W & 3) == 0) && oj >= 0 && oj + 3 < a.W;
+  if (a.out_mode == TB_OUT_LOGITS) {
+    float* o = a.out_num + ((size_t)k * a.H + oi) * a.W;
+    if (vec) {
+      __stcs(reinterpret_cast<float4*>(o + oj), make_float4(q[0], q[1], q[2], q[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (oj + e >= 0 && oj + e < a.W) o[oj + e] = q[e];
+    }
+    return;
+  }
+  if (a.out_mode == TB_OUT_ARGMAX) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool take = (k == 0) || (q[e] > ls.best[e]) || (q[e] != q[e] && ls.best[e] == ls.best[e]);
+      if (take) {
+        ls.best[e] = q[e];
+        ls.arg[e] = k;
+      }
+    }
+    if (k != a.K - 1) return;
+    unsigned char* o = a.out_u8 + (size_t)oi * a.W;
+    if (vec) {
+      *reinterpret_cast<uchar4*>(o + oj) = make_uchar4((unsigned char)ls.arg[0], (unsigned char)ls.arg[1], (unsigned char)ls.arg[2],
+                                                        (unsigned char)ls.arg[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (oj + e >= 0 && oj + e < a.W) o[oj + e] = (unsigned char)ls.arg[e];
+    }
+    return;
+  }
+  // TB_OUT_MASK
+  unsigned char m[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m[e] = (1.f / (1.f + expf(-q[e]))) > a.thr ? 1 : 0;
+  unsigned char* o = a.out_u8 + ((size_t)k * a.H + oi) * a.W;
+  if (vec) {
+    *reinterpret_cast<uchar4*>(o + oj) = make_uchar4(m[0], m[1], m[2], m[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (oj + e >= 0 && oj + e < a.W) o[oj + e] = m[e];
+  }
+}
+
+
+// Base pointers of the per-batch prediction tensors (tb_merge_all_batched) for kernels that use plain loads.
+struct BatchPtrs {
+  const float* p[kMaxTmaBatches];
+};
+
+// single_view.cu: specialised kernels for TTA_NONE (one view: nothing to permute, nothing to stage).
+// Return cudaErrorNotSupported when the geometry is off their lattice (the caller then takes the generic kernels).
+cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptrs, cudaStream_t s);
+cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStream_t s);
+
+}  // namespace tb

@@ -96,6 +96,8 @@ class TiledInferenceEngine:
         bias: Optional[Sequence[float]] = None,
         analytic_weight: bool = False,
         device: Optional[Union[str, torch.device]] = None,
+        activation: Optional[str] = None,
+        temperature: float = 1.0,
     ):
         """
         :param image_shape: (H, W[, C]) of the source image
@@ -106,6 +108,10 @@ class TiledInferenceEngine:
         :param scale, bias: optional per-input-channel affine applied while slicing: x = float(pixel)*scale[c] + bias[c]
         :param analytic_weight: regenerate "pyramid"/"gaussian"/"mean" weights in registers (fp32, <= 3e-7 relative
                to the float64->float32 table) instead of reading the table
+        :param activation, temperature: None | "sigmoid": applied to every prediction BEFORE the TTA view reduction, inside
+               the merge kernel -- what wrapping the model in the reference's ``ApplySigmoidTo(model, temperature=...)``
+               does with two more passes over the prediction stream (inference/ensembling.py:46-68). ("softmax" couples
+               the channels of a pixel: use ``ensembling.ApplySoftmaxTo`` on the model, one extra in-place pass.)
         """
         N.require_cuda("TiledInferenceEngine")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -136,6 +142,10 @@ class TiledInferenceEngine:
         sh, sw = self.slicer.tile_step
         self._grid_dims = (nx, ny, sw, sh, th, tw)
         self._keepalive: List[torch.Tensor] = []
+        if activation not in (None, "none", "sigmoid"):
+            raise ValueError(f"activation must be None or 'sigmoid', got {activation!r}")
+        self._pre = TB.PRE_SIGMOID if activation == "sigmoid" else TB.PRE_NONE
+        self._temperature = float(temperature)
 
     # ------------------------------------------------------------------ image upload
     def to_device(self, image: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
@@ -204,9 +214,11 @@ class TiledInferenceEngine:
         tile_rows: Optional[Tuple[int, int]] = None,
         raw: bool = False,
         init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        output: str = "logits",
+        threshold: float = 0.5,
     ):
         """All predictions -> merged, normalised, cropped logits float32 [K,H,W] (see ``merge_plan`` for the arguments)."""
-        plan = self.merge_plan(preds, out, rows, tile_rows, raw, init)
+        plan = self.merge_plan(preds, out, rows, tile_rows, raw, init, output, threshold)
         result = plan.run()
         # tables / casts must outlive the asynchronous launch: park them until the next call on this engine
         self._keepalive = plan.keep
@@ -220,6 +232,8 @@ class TiledInferenceEngine:
         tile_rows: Optional[Tuple[int, int]] = None,
         raw: bool = False,
         init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        output: str = "logits",
+        threshold: float = 0.5,
     ) -> PreparedLaunch:
         """Prepared launch: all predictions -> merged, normalised, cropped logits float32 [K,H,W].
 
@@ -230,7 +244,15 @@ class TiledInferenceEngine:
         Band mode (multi-GPU strips): ``rows=(y0,y1)`` canvas rows to produce, ``tile_rows=(r0,r1)`` contributing
         tile rows, ``raw=True`` returns un-normalised ``(num [K,y1-y0,Wp], den [y1-y0,Wp])``, ``init`` seeds the
         accumulation with such a pair (the halo received from the previous strip).
+
+        ``output="labels"`` writes ``merged.argmax(0)`` as uint8 [H,W], ``output="mask"`` writes
+        ``merged.sigmoid() > threshold`` as uint8 [K,H,W] straight from the merge epilogue: the float canvas is never
+        written (README.md:225 does this with two more full-canvas passes) and one byte per pixel leaves the GPU.
         """
+        if output not in ("logits", "labels", "mask"):
+            raise ValueError("output must be 'logits', 'labels' or 'mask'")
+        if output != "logits" and raw:
+            raise ValueError("label / mask output needs the normalised (raw=False) mode")
         nx, ny, sw, sh, th, tw = self._grid_dims
         hp, wp = self.slicer.target_shape
         k = self.channels
@@ -296,16 +318,26 @@ class TiledInferenceEngine:
             num = torch.empty((k, y1 - y0, wp), dtype=torch.float32, device=device)
             den = torch.empty((y1 - y0, wp), dtype=torch.float32, device=device)
             out_num, out_den, result = num.data_ptr(), den.data_ptr(), (num, den)
-        else:
+        elif output == "logits":
             if out is None:
                 out = torch.empty((k, h, w), dtype=torch.float32, device=device)
             elif tuple(out.shape) != (k, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous float32 tensor [{k},{h},{w}]")
             out_num, out_den, result = out.data_ptr(), None, out
+        else:
+            u8_shape = (h, w) if output == "labels" else (k, h, w)
+            if out is None:
+                out = torch.empty(u8_shape, dtype=torch.uint8, device=device)
+            elif tuple(out.shape) != u8_shape or out.dtype != torch.uint8 or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous uint8 tensor {u8_shape} for output={output!r}")
+            out_num, out_den, result = None, None, out
+        extra = N.MergeExtra(self._pre, self._temperature,
+                             {"logits": TB.OUT_LOGITS, "labels": TB.OUT_ARGMAX, "mask": TB.OUT_MASK}[output], float(threshold),
+                             out.data_ptr() if (output != "logits" and not raw) else None)
         grid_ref = C.byref(grid)
         common = (k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1, N.ptr(init_num), N.ptr(init_den),
-                  1 if raw else 0, top, left, h, w, out_num, out_den, N.stream_ptr(device))
-        keep += [grid, self._weight, self._weight_table, result]
+                  1 if raw else 0, top, left, h, w, out_num, out_den, C.byref(extra), N.stream_ptr(device))
+        keep += [grid, self._weight, self._weight_table, result, extra]
         if mode == "batched":
             ptr_arr = (C.c_void_p * len(batches))(*[b.data_ptr() for b in batches])
             keep.append(ptr_arr)
@@ -313,11 +345,11 @@ class TiledInferenceEngine:
 
             def to_table():  # geometry off the TMA lattice -> pointer-table kernel
                 pointer_table()
-                return N.lib().tb_merge_all, (None, grid_ref) + common, "tb_merge_all"
+                return N.lib().tb_merge_all_ex, (None, grid_ref) + common, "tb_merge_all_ex"
 
-            return PreparedLaunch(N.lib().tb_merge_all_batched, args, keep, result, device, "tb_merge_all_batched", to_table)
+            return PreparedLaunch(N.lib().tb_merge_all_batched_ex, args, keep, result, device, "tb_merge_all_batched_ex", to_table)
         args = (pred_ptr, grid_ref) + common
-        return PreparedLaunch(N.lib().tb_merge_all, args, keep, result, device, "tb_merge_all")
+        return PreparedLaunch(N.lib().tb_merge_all_ex, args, keep, result, device, "tb_merge_all_ex")
 
     # ------------------------------------------------------------------ output side
     def labels(self, logits: torch.Tensor, mode: str = "argmax", threshold: float = 0.5,
@@ -348,9 +380,10 @@ class TiledInferenceEngine:
     # ------------------------------------------------------------------ whole pipeline
     @torch.no_grad()
     def predict(self, image: Union[np.ndarray, torch.Tensor], model: Callable[[torch.Tensor], torch.Tensor],
-                batch_size: Optional[int] = None, layout: str = "HWC") -> torch.Tensor:
-        """image (host or device) -> [K,H,W] float32 logits on the GPU. ``batch_size`` counts tiles (each
-        contributes A views to the model batch); None = all tiles in one model call."""
+                batch_size: Optional[int] = None, layout: str = "HWC", output: str = "logits",
+                threshold: float = 0.5) -> torch.Tensor:
+        """image (host or device) -> [K,H,W] float32 logits on the GPU (or the uint8 class map / masks, see ``merge_plan``).
+        ``batch_size`` counts tiles (each contributes A views to the model batch); None = all tiles in one model call."""
         image = self.to_device(image)
         batch_size = self.num_tiles if batch_size is None else int(batch_size)
         outputs = []
@@ -360,7 +393,7 @@ class TiledInferenceEngine:
             if pred.dtype != torch.float32:
                 pred = pred.float()
             outputs.append(pred.contiguous())
-        return self.merge(outputs[0] if len(outputs) == 1 else outputs)
+        return self.merge(outputs[0] if len(outputs) == 1 else outputs, output=output, threshold=threshold)
 
     # ------------------------------------------------------------------ host -> host, pipelined over tile rows
     @torch.no_grad()
@@ -369,8 +402,8 @@ class TiledInferenceEngine:
                         output: str = "logits", threshold: float = 0.5) -> torch.Tensor:
         """Pinned host image -> pinned host logits [K,H,W], software-pipelined over chunks of tile rows.
 
-        ``output="labels"`` / ``"mask"`` convert every finished band with ``labels()`` on the GPU and
-        download uint8 [H,W] / [K,H,W] instead: 1 byte per pixel crosses PCIe instead of 4*K.
+        ``output="labels"`` / ``"mask"``: every finished band leaves the merge epilogue as the uint8 class map [H,W] /
+        masks [K,H,W] (no float canvas at all), so 1 byte per pixel crosses PCIe instead of 4*K.
 
         For every chunk: (copy stream A) upload the image rows the chunk needs; (compute stream) slice+augment, model,
         merge the canvas rows that are now final (band mode of tb_merge_all_batched over the model outputs so far);
@@ -397,9 +430,10 @@ class TiledInferenceEngine:
             raise ValueError(f"out_host must be uint8 {u8_shape} for output={output!r}")
         if not hasattr(self, "_pipe"):
             self._pipe = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
-                              image=torch.empty(image_host.shape, dtype=image_host.dtype, device=dev),
-                              out=torch.empty((k, h, w), dtype=torch.float32, device=dev))
+                              image=torch.empty(image_host.shape, dtype=image_host.dtype, device=dev), out=None)
         pipe = self._pipe
+        if output == "logits" and pipe["out"] is None:  # the float canvas exists only when float logits are asked for
+            pipe["out"] = torch.empty((k, h, w), dtype=torch.float32, device=dev)
         image_dev, out_dev = pipe["image"], pipe["out"]
         u8_dev = None
         if output != "logits":
@@ -429,11 +463,11 @@ class TiledInferenceEngine:
             y = model(x)
             outputs.append(y if y.dtype == torch.float32 and y.is_contiguous() else y.float().contiguous())
             y_cur = hp if rb == ny else rb * sh
-            self.merge(outputs, out=out_dev, rows=(merged_until, y_cur), tile_rows=(0, rb))
+            # finished band -> float logits, or (fused in the merge epilogue) the uint8 class map / masks: 1 byte per pixel
+            self.merge(outputs, out=out_dev if u8_dev is None else u8_dev, rows=(merged_until, y_cur), tile_rows=(0, rb),
+                       output=output, threshold=threshold)
             o0, o1 = max(merged_until - top, 0), min(y_cur - top, h)
             if o1 > o0:
-                if u8_dev is not None:  # finished band -> class map / masks on the GPU, 1 byte per pixel to download
-                    self.labels(out_dev, "argmax" if output == "labels" else "threshold", threshold, out=u8_dev, rows=(o0, o1))
                 ev2 = torch.cuda.Event()
                 ev2.record(main)
                 pipe["d2h"].wait_event(ev2)
