@@ -252,12 +252,34 @@ TB_API int tb_merge_all_batched(const float* const* batch_ptrs_host, int n_batch
  *                       pixel leaves the GPU; out_num may be NULL in these modes. */
 enum tb_pre_activation { TB_PRE_NONE = 0, TB_PRE_SIGMOID = 1 };
 enum tb_out_mode { TB_OUT_LOGITS = 0, TB_OUT_ARGMAX = 1, TB_OUT_MASK = 2 };
+
+/* Multi-GPU "ragged strips" (new relative to the reference, whose TileMerger is single-device, tiles.py:306-308):
+ * the rank holds the predictions of the row-major tile range [t0,t1) (= the batched call's first_tile / covered tiles).
+ * A 32x32 canvas block whose LAST covering tile is ours is FINAL here; if earlier covering tiles belong to lower ranks its
+ * accumulation starts from `seed_*` (partial sums the previous rank stored there through NVLink); if later covering tiles
+ * belong to higher ranks the block is a SPILL and its un-normalised sums are stored to `spill_*` (= the next rank's seed
+ * buffers, peer memory) instead of any output. Row windows: buffer row 0 is canvas row seed_y0 / spill_y0, all Wp columns.
+ * phase_mask selects which block classes one launch processes, so that the caller can order them around the flags:
+ *   1 final unseeded | 2 spill unseeded | 4 final seeded | 8 spill seeded        (tb_peer_signal / tb_peer_wait below)
+ * Only the lattice kernels (TMA ring, single view) implement it: TB_ERR_UNSUPPORTED otherwise. */
+typedef struct tb_peer_plan {
+  int phase_mask;
+  int t0, t1;
+  const float* seed_num; /* f32 [K, seed_rows, Wp] */
+  const float* seed_den; /* f32 [seed_rows, Wp] */
+  int seed_y0, seed_rows;
+  float* spill_num;      /* f32 [K, spill_rows, Wp] */
+  float* spill_den;      /* f32 [spill_rows, Wp] */
+  int spill_y0, spill_rows;
+} tb_peer_plan;
+
 typedef struct tb_merge_extra {
   int pre;
   float temperature;
   int out_mode;
   float threshold;
   uint8_t* out_u8;
+  const tb_peer_plan* peer; /* NULL: single-GPU / legacy band mode */
 } tb_merge_extra;
 
 TB_API int tb_merge_all_ex(const float* pred, const tb_grid* grid, int K, int tta, int reduction, const tb_weight* weight,
@@ -269,6 +291,27 @@ TB_API int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_ba
                                    int Hp, int Wp, int y0, int y1, int r0, int r1, const float* init_num, const float* init_den,
                                    int raw, int top, int left, int H, int W, float* out_num, float* out_den,
                                    const tb_merge_extra* ex, void* stream);
+
+/* ---- peer memory for the multi-GPU halo: the one place where the library owns device memory (cudaMalloc'ed so that it
+ * can be exported with CUDA IPC; torch's caching allocator sub-allocates and cannot). One process per GPU; a rank
+ * allocates its mailbox (seed buffers + flags), exports the 64-byte handle, the neighbour opens it and gets a pointer
+ * it can store to from its kernels over NVLink (or into the same GPU when two ranks share one in tests).
+ *   tb_peer_alloc   cudaMalloc + zero fill;  tb_peer_free
+ *   tb_peer_export  handle_out: 64 bytes (cudaIpcMemHandle_t);  tb_peer_open / tb_peer_close in ANOTHER process
+ *   tb_peer_signal  stream-ordered: after everything queued before it on `stream` has completed, store `value` to *flag
+ *                   with system scope (flag may be peer memory)
+ *   tb_peer_wait    stream-ordered: hold the stream until *flag >= value (acquire, system scope). Gives up after timeout_ms
+ *                   (then stores the observed value + 1 into *status, if given, and lets the stream continue, so that a
+ *                   dead neighbour cannot hang the GPU); *status stays 0 on success. */
+TB_API int tb_peer_alloc(size_t bytes, void** dev_ptr_out);
+TB_API int tb_peer_free(void* dev_ptr);
+TB_API int tb_peer_export(const void* dev_ptr, void* handle_out_64);
+TB_API int tb_peer_open(const void* handle_64, void** dev_ptr_out);
+TB_API int tb_peer_close(void* dev_ptr);
+TB_API int tb_peer_signal(uint64_t* flag, uint64_t value, void* stream);
+TB_API int tb_peer_wait(const uint64_t* flag, uint64_t value, int timeout_ms, uint64_t* status, void* stream);
+/* synchronous read of one flag / status word (device or mapped peer memory) into host memory */
+TB_API int tb_peer_read(const uint64_t* word, uint64_t* value_out_host);
 
 /* ------------------------------------------------------------------------------------------------
  * LOSSES  (forward value + gradient w.r.t. the logits in one call)

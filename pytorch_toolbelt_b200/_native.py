@@ -87,11 +87,20 @@ class Grid(C.Structure):
     ]
 
 
+class PeerPlan(C.Structure):
+    """tb_peer_plan (include/tb200.h): multi-GPU ragged strips -- which block classes a launch processes and where the
+    seed (read) / spill (peer write) partial sums live."""
+
+    _fields_ = [("phase_mask", C.c_int), ("t0", C.c_int), ("t1", C.c_int), ("seed_num", C.c_void_p), ("seed_den", C.c_void_p),
+                ("seed_y0", C.c_int), ("seed_rows", C.c_int), ("spill_num", C.c_void_p), ("spill_den", C.c_void_p),
+                ("spill_y0", C.c_int), ("spill_rows", C.c_int)]
+
+
 class MergeExtra(C.Structure):
-    """tb_merge_extra (include/tb200.h): pre-activation before the view reduction, label / mask output modes."""
+    """tb_merge_extra (include/tb200.h): pre-activation before the view reduction, label / mask output modes, peer plan."""
 
     _fields_ = [("pre", C.c_int), ("temperature", C.c_float), ("out_mode", C.c_int), ("threshold", C.c_float),
-                ("out_u8", C.c_void_p)]
+                ("out_u8", C.c_void_p), ("peer", C.POINTER(PeerPlan))]
 
 
 class FocalParams(C.Structure):
@@ -157,6 +166,14 @@ SIGNATURES = {
         [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
          _i, _i, _vp, _vp, C.POINTER(MergeExtra), _vp],
     ),
+    "tb_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),
+    "tb_peer_free": (_i, [_vp]),
+    "tb_peer_export": (_i, [_vp, _vp]),
+    "tb_peer_open": (_i, [_vp, C.POINTER(C.c_void_p)]),
+    "tb_peer_close": (_i, [_vp]),
+    "tb_peer_signal": (_i, [_vp, C.c_uint64, _vp]),
+    "tb_peer_wait": (_i, [_vp, C.c_uint64, _i, _vp, _vp]),
+    "tb_peer_read": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "tb_loss_workspace_bytes": (_sz, [_i64, _i, _i64]),
     "tb_focal_fwd_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i64, C.POINTER(FocalParams), _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb_softmax_focal_fwd_bwd": (

@@ -32,8 +32,10 @@ __device__ __forceinline__ void ldcs4(const float* p, float v[4]) {
 // merge
 // ---------------------------------------------------------------------------------------------------------------
 // UW = unit width in pixels (128: Tw and Sx multiples of 128; 32 otherwise). SEP: separable in-register gaussian.
-template <int UW, bool SEP>
-__global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
+// PLAIN: mean / sum reduction and no pre-activation (one view: the value itself): no per-element switch.
+// gridDim.y > 1: one row pass per CTA (small problems: 4x the CTAs, a quarter of the dependent load rounds per CTA).
+template <int UW, bool SEP, bool PLAIN>
+__global__ void __launch_bounds__(kSV, 3) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
                                                                   int nux, int ux0) {
   constexpr int LPR = UW / 4;        // lanes per unit row
   constexpr int RPP = kSV / LPR;     // rows per pass
@@ -56,6 +58,12 @@ __global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs 
   }
   __syncthreads();
   const int ra = sh[0], rb = sh[1], ca = sh[2], cb = sh[3];
+  int cls = 0;
+  if (a.peer.phase_mask) {  // multi-GPU ragged strips: is this block ours, seeded, a spill? (uniform over the CTA)
+    cls = peer_block_class(a.peer, g.nx, ra, rb, ca, cb);
+    if (!cls) return;
+  }
+  const bool seeded = cls & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), spill = cls & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
   const int lc = threadIdx.x % LPR, row0 = threadIdx.x / LPR;
   const int x = X0 + 4 * lc;
   if (x >= a.Wp) return;  // (after the only barrier)
@@ -63,23 +71,23 @@ __global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs 
   const size_t plane = (size_t)g.Th * g.Tw;
   const bool one_batch = a.batch_tiles >= a.covered_tiles;
 
-  // separable gaussian: w(i,j) = exp(-di^2 c) * exp(-dj^2 c); the column factors of the (<= 4) covering tile columns
-  float wj[4][4];
+  // separable gaussian: w(i,j) = exp(-di^2 c) * exp(-dj^2 c); the column factors of the (<= 2) covering tile columns
+  // live in registers (selected by compare, never indexed: a runtime index would push the array to local memory)
+  float wj0[4] = {0.f, 0.f, 0.f, 0.f}, wj1[4] = {0.f, 0.f, 0.f, 0.f};
   if (SEP) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = ca + u;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float dj = (float)(x - c * g.Sx + e) - a.w.wc;
-        wj[u][e] = (c <= cb) ? __expf(-(dj * dj) * a.w.param) : 0.f;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = (float)(x - ca * g.Sx + e) - a.w.wc;
+      const float d1 = (float)(x - (ca + 1) * g.Sx + e) - a.w.wc;
+      wj0[e] = __expf(-(d0 * d0) * a.w.param);
+      wj1[e] = __expf(-(d1 * d1) * a.w.param);
     }
   }
 
   // row pass outside, channel inside: the running argmax of the label epilogue then lives in one LabelState
+  const int p_begin = gridDim.y > 1 ? (int)blockIdx.y : 0, p_end = gridDim.y > 1 ? p_begin + 1 : PASSES;
 #pragma unroll 1
-  for (int p = 0; p < PASSES; ++p) {
+  for (int p = p_begin; p < p_end; ++p) {
     const int y = Y0 + row0 + p * RPP;
     if (y < a.y0 || y >= a.y1) continue;
     LabelState ls;
@@ -89,6 +97,13 @@ __global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs 
         const size_t o = (size_t)(y - a.y0) * a.Wp + x;
         ldcs4(a.init_num + (size_t)k * rows * a.Wp + o, acc);
         ldcs4(a.init_den + o, den);
+      }
+      if (seeded) {
+        const size_t o = (size_t)(y - a.peer.seed_y0) * a.Wp + x;
+        const float4 n4 = __ldcg(reinterpret_cast<const float4*>(a.peer.seed_num + (size_t)k * a.peer.seed_rows * a.Wp + o));
+        const float4 d4 = __ldcg(reinterpret_cast<const float4*>(a.peer.seed_den + o));
+        acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
+        den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
       int r = ra, c = ca;
       while (r <= rb) {
@@ -111,9 +126,9 @@ __global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs 
               if (SEP) {
                 const float di = (float)i - a.w.hc;
                 const float wi = __expf(-(di * di) * a.w.param);
-                const int cu = c - ca;  // < 4 on this path (host checks)
+                const bool first_col = (c == ca);  // <= 2 covering columns on this path (host checks)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) wv[u][e] = wi * wj[cu & 3][e];
+                for (int e = 0; e < 4; ++e) wv[u][e] = wi * (first_col ? wj0[e] : wj1[e]);
               } else if (a.w.kind == TB_W_TABLE) {
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)i * g.Tw + j));
                 wv[u][0] = w4.x; wv[u][1] = w4.y; wv[u][2] = w4.z; wv[u][3] = w4.w;
@@ -133,14 +148,19 @@ __global__ void __launch_bounds__(kSV, 4) merge_single_view_kernel(MergeAllArgs 
           if (ok[u]) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float val = red_post<float>(a.red, red_pre<float>(a.red, pre_act(a.pre, a.temperature, pv[u][e])), 1);
+              const float val = PLAIN ? pv[u][e]
+                                      : red_post<float>(a.red, red_pre<float>(a.red, pre_act(a.pre, a.temperature, pv[u][e])), 1);
               acc[e] = add_rn(acc[e], mul_rn(val, wv[u][e]));
               den[e] = add_rn(den[e], wv[u][e]);
             }
           }
         }
       }
-      if (a.raw) {
+      if (spill) {
+        const size_t o = (size_t)(y - a.peer.spill_y0) * a.Wp + x;
+        *reinterpret_cast<float4*>(a.peer.spill_num + (size_t)k * a.peer.spill_rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (k == 0) *reinterpret_cast<float4*>(a.peer.spill_den + o) = make_float4(den[0], den[1], den[2], den[3]);
+      } else if (a.raw) {
         const size_t o = (size_t)(y - a.y0) * a.Wp + x;
         *reinterpret_cast<float4*>(a.out_num + (size_t)k * rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (k == 0) *reinterpret_cast<float4*>(a.out_den + o) = make_float4(den[0], den[1], den[2], den[3]);
@@ -165,18 +185,25 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   const bool wide = (g.Tw % 128 == 0) && (g.Sx % 128 == 0);
   const int uw = wide ? 128 : 32;
   const int cover_cols = (g.Tw + g.Sx - 1) / g.Sx;
-  const bool sep = a.w.kind == TB_W_GAUSSIAN && cover_cols <= 4;
+  const bool sep = a.w.kind == TB_W_GAUSSIAN && cover_cols <= 2;
+  const bool plain = (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) && a.pre == TB_PRE_NONE;
   const int xa = a.raw ? 0 : a.left, xb = a.raw ? a.Wp : a.left + a.W;
   const int ux0 = xa / uw, nux = (xb + uw - 1) / uw - ux0;
   const long long units = (long long)nux * a.nby;
   if (units <= 0 || units >= (1ll << 31)) return cudaErrorNotSupported;
+  // few units (small images): one row pass per CTA, so that the grid still fills the GPU several times over
+  const int passes = wide ? 4 : 1;
+  const bool split = passes > 1 && units < (long long)sm_count() * 4 * 8;
+  const dim3 grid((unsigned)units, split ? passes : 1);
+#define TB_SV(UW, SEP_, PLAIN_) merge_single_view_kernel<UW, SEP_, PLAIN_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
   if (wide) {
-    if (sep) merge_single_view_kernel<128, true><<<(unsigned)units, kSV, 0, s>>>(a, ptrs, nux, ux0);
-    else merge_single_view_kernel<128, false><<<(unsigned)units, kSV, 0, s>>>(a, ptrs, nux, ux0);
+    if (sep) { if (plain) TB_SV(128, true, true); else TB_SV(128, true, false); }
+    else { if (plain) TB_SV(128, false, true); else TB_SV(128, false, false); }
   } else {
-    if (sep) merge_single_view_kernel<32, true><<<(unsigned)units, kSV, 0, s>>>(a, ptrs, nux, ux0);
-    else merge_single_view_kernel<32, false><<<(unsigned)units, kSV, 0, s>>>(a, ptrs, nux, ux0);
+    if (sep) { if (plain) TB_SV(32, true, true); else TB_SV(32, true, false); }
+    else { if (plain) TB_SV(32, false, true); else TB_SV(32, false, false); }
   }
+#undef TB_SV
   return cudaGetLastError();
 }
 

@@ -1179,6 +1179,7 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
       const uint64_t policy = hint ? l2_evict_first_policy() : 0ull;
       for (int blk = blk0; blk < nblocks; blk += blk_step) {
         const BlockWork w = block_work(a, blk);
+        if (a.peer.phase_mask && !peer_block_class(a.peer, g.nx, w.ra, w.rb, w.ca, w.cb)) continue;  // (same test as the consumers)
         const int nt = block_tile_count(a, w);
         for (int k = 0; k < a.K; ++k) {
           int idx = 0, s = 0;
@@ -1228,6 +1229,12 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
   LabelState ls;
   for (int blk = blk0; blk < nblocks; blk += blk_step) {
     const BlockWork w = block_work(a, blk);
+    int cls = 0;
+    if (a.peer.phase_mask) {
+      cls = peer_block_class(a.peer, g.nx, w.ra, w.rb, w.ca, w.cb);
+      if (!cls) continue;
+    }
+    const bool seeded = cls & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), spill = cls & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
     const int nt = block_tile_count(a, w);
     const int y = w.Y0 + li;
     const bool y_ok = (y >= a.y0 && y < a.y1);
@@ -1237,6 +1244,13 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
         const size_t o = (size_t)(y - a.y0) * a.Wp + w.X0 + lj;
         const float4 n4 = *reinterpret_cast<const float4*>(a.init_num + (size_t)k * rows * a.Wp + o);
         const float4 d4 = *reinterpret_cast<const float4*>(a.init_den + o);
+        acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
+        den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
+      }
+      if (seeded && y_ok) {  // partial sums of the lower ranks' tiles (written by the previous rank through NVLink)
+        const size_t o = (size_t)(y - a.peer.seed_y0) * a.Wp + w.X0 + lj;
+        const float4 n4 = __ldcg(reinterpret_cast<const float4*>(a.peer.seed_num + (size_t)k * a.peer.seed_rows * a.Wp + o));
+        const float4 d4 = __ldcg(reinterpret_cast<const float4*>(a.peer.seed_den + o));
         acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
         den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
@@ -1283,7 +1297,11 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
         }
       }
       if (!y_ok) continue;
-      if (a.raw) {
+      if (spill) {  // later covering tiles live on higher ranks: hand the partial sums to the next rank (peer stores)
+        const size_t o = (size_t)(y - a.peer.spill_y0) * a.Wp + w.X0 + lj;
+        *reinterpret_cast<float4*>(a.peer.spill_num + (size_t)k * a.peer.spill_rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (k == 0) *reinterpret_cast<float4*>(a.peer.spill_den + o) = make_float4(den[0], den[1], den[2], den[3]);
+      } else if (a.raw) {
         const size_t o = (size_t)(y - a.y0) * a.Wp + w.X0 + lj;
         *reinterpret_cast<float4*>(a.out_num + (size_t)k * rows * a.Wp + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (k == 0) *reinterpret_cast<float4*>(a.out_den + o) = make_float4(den[0], den[1], den[2], den[3]);
@@ -1949,6 +1967,20 @@ static int apply_merge_extra(const tb_merge_extra* ex, int raw, int K, float*& o
   }
   a->out_num = out_num;
   a->vec_ok = aligned16(out_num) && (!a->out_u8 || (reinterpret_cast<uintptr_t>(a->out_u8) & 3) == 0);
+  a->peer = PeerPlan{};
+  if (ex && ex->peer && ex->peer->phase_mask) {
+    const tb_peer_plan& p = *ex->peer;
+    TB_REQUIRE(!raw, TB_ERR_ARG, "tb_merge_all: the peer plan replaces the raw band mode");
+    TB_REQUIRE(p.phase_mask > 0 && p.phase_mask < 16 && p.t0 >= 0 && p.t0 < p.t1, TB_ERR_ARG, "tb_merge_all: bad peer plan");
+    const bool reads = p.phase_mask & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), writes = p.phase_mask & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
+    TB_REQUIRE(!reads || (p.seed_num && p.seed_den && p.seed_rows > 0 && aligned16(p.seed_num) && aligned16(p.seed_den)),
+               TB_ERR_ARG, "tb_merge_all: seeded phases need 16-byte aligned seed buffers");
+    TB_REQUIRE(!writes || (p.spill_num && p.spill_den && p.spill_rows > 0 && aligned16(p.spill_num) && aligned16(p.spill_den)),
+               TB_ERR_ARG, "tb_merge_all: spill phases need 16-byte aligned spill buffers");
+    a->peer.phase_mask = p.phase_mask; a->peer.t0 = p.t0; a->peer.t1 = p.t1;
+    a->peer.seed_num = p.seed_num; a->peer.seed_den = p.seed_den; a->peer.seed_y0 = p.seed_y0; a->peer.seed_rows = p.seed_rows;
+    a->peer.spill_num = p.spill_num; a->peer.spill_den = p.spill_den; a->peer.spill_y0 = p.spill_y0; a->peer.spill_rows = p.spill_rows;
+  }
   return TB_OK;
 }
 
@@ -2045,6 +2077,7 @@ int tb_merge_all_ex(const float* pred, const tb_grid* grid, int K, int tta, int 
       return TB_OK;
     }
   }
+  TB_REQUIRE(!a.peer.phase_mask, TB_ERR_UNSUPPORTED, "tb_merge_all: the peer plan needs the lattice kernels (Th, Tw, Sx, Sy % 32 == 0)");
   if (al || al_tbl) {
     TB_DISPATCH_TTA(tta, merge_all_kernel<true, TTA_><<<(unsigned)blocks, kThreads, 0, s>>>(a));
   } else {

@@ -21,6 +21,38 @@ struct SliceArgs {
 };
 
 
+// Multi-GPU "ragged strips" (distributed/ragged.py): this rank holds the predictions of the row-major tile range [t0,t1).
+// A canvas block is FINAL here iff its last covering tile (row-major order) is ours; if earlier covering tiles belong to
+// lower ranks the accumulation starts from their partial sums (SEEDED: read from `seed_*`, which the previous rank filled
+// through NVLink peer stores); if later covering tiles belong to higher ranks the block is a SPILL: the un-normalised
+// partial sums go to `spill_*` = the next rank's seed buffers (peer memory). Tile order -- and therefore every rounding --
+// is the single-GPU order, so the sharded result is bit-identical. phase_mask == 0 disables all of this.
+enum : int { TB_PH_FINAL = 1, TB_PH_SPILL = 2, TB_PH_SEEDED_FINAL = 4, TB_PH_SEEDED_SPILL = 8 };
+struct PeerPlan {
+  int phase_mask;   // which block classes this launch processes (bits above)
+  int t0, t1;
+  const float* seed_num;  // [K, seed_rows, Wp]
+  const float* seed_den;  // [seed_rows, Wp]
+  int seed_y0, seed_rows;
+  float* spill_num;       // [K, spill_rows, Wp] (peer)
+  float* spill_den;       // [spill_rows, Wp]    (peer)
+  int spill_y0, spill_rows;
+};
+
+// Block class (0 = not ours / filtered out). (ra..rb, ca..cb) = ALL covering tile rows / columns of the block.
+__device__ __forceinline__ int peer_block_class(const PeerPlan& p, int nx, int ra, int rb, int ca, int cb) {
+  bool own = false;
+  for (int r = ra; r <= rb && !own; ++r) {
+    // row r covers tile indices [r*nx+ca, r*nx+cb]: intersects [t0,t1)?
+    own = (r * nx + ca < p.t1) && (r * nx + cb >= p.t0);
+  }
+  if (!own) return 0;
+  const bool seeded = ra * nx + ca < p.t0;
+  const bool spill = rb * nx + cb >= p.t1;
+  const int cls = seeded ? (spill ? TB_PH_SEEDED_SPILL : TB_PH_SEEDED_FINAL) : (spill ? TB_PH_SPILL : TB_PH_FINAL);
+  return (p.phase_mask & cls) ? cls : 0;
+}
+
 struct MergeAllArgs {
   const float* pred;
   tb_grid grid;
@@ -43,6 +75,7 @@ struct MergeAllArgs {
   float thr;
   unsigned char* out_u8;
   int vec_ok;         // out_num 16-byte / out_u8 4-byte aligned: vector stores allowed
+  PeerPlan peer;
 };
 
 __device__ __forceinline__ float pre_act(int pre, float T, float v) {

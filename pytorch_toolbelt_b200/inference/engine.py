@@ -234,6 +234,8 @@ class TiledInferenceEngine:
         init: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
         output: str = "logits",
         threshold: float = 0.5,
+        first_tile: Optional[int] = None,
+        peer: Optional[dict] = None,
     ) -> PreparedLaunch:
         """Prepared launch: all predictions -> merged, normalised, cropped logits float32 [K,H,W].
 
@@ -276,7 +278,10 @@ class TiledInferenceEngine:
         keep += batches
         sizes = [b.shape[0] // self.views for b in batches]
         total = sum(sizes)
-        if total == self.num_tiles:
+        if first_tile is not None:  # an explicit row-major tile range is resident (multi-GPU ragged strips)
+            if first_tile < 0 or first_tile + total > self.num_tiles:
+                raise ValueError(f"tiles [{first_tile},{first_tile + total}) outside the grid of {self.num_tiles}")
+        elif total == self.num_tiles:
             first_tile = 0  # the whole grid is resident; tile_rows (if any) only restricts who contributes
         elif tile_rows is not None and total == (r1 - r0) * nx:
             first_tile = r0 * nx  # only this strip's tiles are resident (multi-GPU)
@@ -285,7 +290,7 @@ class TiledInferenceEngine:
                              + (f" or the strip's {(r1 - r0) * nx}" if tile_rows is not None else ""))
         device = batches[0].device
         uniform = all(sz == sizes[0] for sz in sizes[:-1]) and sizes[-1] <= sizes[0]
-        whole_grid_single = len(batches) == 1 and sizes[0] == self.num_tiles
+        whole_grid_single = len(batches) == 1 and sizes[0] == self.num_tiles and first_tile == 0
         mode = "single" if whole_grid_single else ("batched" if uniform else "table")
 
         def pointer_table():
@@ -331,9 +336,19 @@ class TiledInferenceEngine:
             elif tuple(out.shape) != u8_shape or out.dtype != torch.uint8 or not out.is_contiguous():
                 raise ValueError(f"out must be a contiguous uint8 tensor {u8_shape} for output={output!r}")
             out_num, out_den, result = None, None, out
+        peer_ref = None
+        if peer is not None:
+            if peer["t0"] != first_tile or peer["t1"] != first_tile + total:
+                raise ValueError("peer plan tile range must equal the resident tile range")
+            peer_struct = N.PeerPlan(int(peer["phase_mask"]), int(peer["t0"]), int(peer["t1"]), peer.get("seed_num"),
+                                     peer.get("seed_den"), int(peer.get("seed_y0", 0)), int(peer.get("seed_rows", 0)),
+                                     peer.get("spill_num"), peer.get("spill_den"), int(peer.get("spill_y0", 0)),
+                                     int(peer.get("spill_rows", 0)))
+            keep.append(peer_struct)
+            peer_ref = C.pointer(peer_struct)
         extra = N.MergeExtra(self._pre, self._temperature,
                              {"logits": TB.OUT_LOGITS, "labels": TB.OUT_ARGMAX, "mask": TB.OUT_MASK}[output], float(threshold),
-                             out.data_ptr() if (output != "logits" and not raw) else None)
+                             out.data_ptr() if (output != "logits" and not raw) else None, peer_ref)
         grid_ref = C.byref(grid)
         common = (k, self.tta, self.reduction, C.byref(self._weight), hp, wp, y0, y1, r0, r1, N.ptr(init_num), N.ptr(init_den),
                   1 if raw else 0, top, left, h, w, out_num, out_den, C.byref(extra), N.stream_ptr(device))
