@@ -320,7 +320,7 @@ TB_API int tb_peer_read(const uint64_t* word, uint64_t* value_out_host);
  * loss_out / stats_out are device pointers; the value is complete when the stream reaches that point.
  * ---------------------------------------------------------------------------------------------- */
 
-enum tb_loss_reduction { TB_LOSS_NONE = 0, TB_LOSS_MEAN = 1, TB_LOSS_SUM = 2, TB_LOSS_BATCHWISE = 3 };
+enum tb_loss_reduction { TB_LOSS_NONE = 0, TB_LOSS_MEAN = 1, TB_LOSS_SUM = 2, TB_LOSS_BATCHWISE = 3, TB_LOSS_NORMALIZED = 4 };
 enum tb_target_kind { TB_T_DENSE_F32 = 0, TB_T_LABELS_I64 = 1 };
 
 typedef struct tb_focal_params {
@@ -402,14 +402,40 @@ TB_API int tb_wing_fwd_bwd(const float* x, const float* t, int64_t n, float widt
  * gradient (a device scalar) to a stored gradient buffer without a host synchronisation. */
 TB_API int tb_scale_by_device_scalar(float* data, int64_t n, const float* scale_dev, void* stream);
 
-/* Lovasz: given errors already sorted descending with their ground-truth bits (gt_sorted f32 0/1) for
- * `segs` independent segments (offsets int64 [segs+1]), compute per segment loss = dot(relu?(err), lovasz_grad)
- * and the per-position Lovasz gradient (lovasz.py:23-34,55-72,112-140).
- *   relu != 0: hinge variant (relu on errors, lovasz.py:71); grad_sorted f32 [total] receives g_k (masked by
- *   err>0 for hinge); seg_loss f32 [segs]. */
-TB_API int tb_lovasz_sorted(const float* err_sorted, const float* gt_sorted, const int64_t* seg_offsets_host, int segs,
-                     int relu, float* seg_loss, float* grad_sorted, void* ws, size_t ws_bytes, void* stream);
-TB_API size_t tb_lovasz_workspace_bytes(int64_t total, int segs);
+/* the reference's remaining element-wise losses on the same fused forward+gradient skeleton.
+ *   kind 0  SoftBCEWithLogitsLoss (soft_bce.py:9-50): label smoothing (has_smooth / smooth), ignore_index, `weight` and
+ *           `pos_weight` (device f32, weight_n / pos_weight_n = 1 or C entries, indexed by channel), reduction none|mean|sum
+ *   kind 1  balanced_binary_cross_entropy_with_logits (balanced_bce.py:10-49): the counts of t == 1 and t == 0 are taken
+ *           by a first pass over t (device-side, no host sync), `gamma`, ignore_index, reduction none|mean|sum
+ *   kind 2  QualityFocalLoss (quality_focal_loss.py:5-53): `beta`, reduction none|mean|sum|TB_LOSS_NORMALIZED (sum L / sum F,
+ *           gradient through both sums: two passes)
+ * x, t f32 [B,C,inner]; loss_out f32 [1] (or [B,C,inner] element losses for TB_LOSS_NONE); grad f32 [B,C,inner] or NULL
+ * (= d loss / d x, already divided by numel for MEAN); ws: tb_loss_workspace_bytes(B, C, inner). */
+typedef struct tb_elem_loss_params {
+  int kind;
+  int reduction;
+  float smooth;
+  int has_smooth;
+  float ignore_index;
+  int has_ignore;
+  int weight_n;
+  int pos_weight_n;
+  float gamma;
+  float beta;
+} tb_elem_loss_params;
+TB_API int tb_elem_loss_fwd_bwd(const float* x, const float* t, int64_t B, int C, int64_t inner, const tb_elem_loss_params* p,
+                         const float* weight, const float* pos_weight, float* loss_out, float* grad, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* soft F1 losses (soft_f1.py:8-107) on [N,C] logits (element (n,c) at x[n*C+c]):
+ *   mode 0  BinarySoftF1Loss: C == 1, t f32 [N]; rows whose target equals `ignore` are dropped; p = clamp(sigmoid(x), eps, 1-eps)
+ *   mode 1  SoftF1Loss: t i64 [N] class labels, p = clamp(softmax(x, 1), eps, 1-eps), per-class soft F1, mean over classes
+ *   mode 2  SoftF1Loss with ignore_index: the reference compares the ONE-HOT VALUES with ignore_index and flattens what is
+ *           kept into one F1 (soft_f1.py:97-106); replicated literally
+ * loss_out f32 [1]; grad f32 [N,C] or NULL. C <= 64. */
+TB_API size_t tb_soft_f1_workspace_bytes(int64_t N, int C);
+TB_API int tb_soft_f1_fwd_bwd(const float* x, const void* t, int64_t N, int C, int mode, int has_ignore, float ignore, float eps,
+                       float* loss_out, float* grad, void* ws, size_t ws_bytes, void* stream);
 
 /* Lovasz hinge (mode 0; BinaryLovaszLoss, lovasz.py:37-86,187-194) and Lovasz-softmax (mode 1; LovaszLoss with
  * classes="present", lovasz.py:92-160,197-204) as ONE launch sequence for all (image, class) segments: errors + sort keys,

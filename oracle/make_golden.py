@@ -26,6 +26,7 @@ from pytorch_toolbelt.inference import tta as RA  # noqa: E402
 from pytorch_toolbelt import losses as RL  # noqa: E402
 from pytorch_toolbelt.losses import functional as RLF  # noqa: E402
 
+from oracle import losses_extra_oracle as LE  # noqa: E402
 from oracle import losses_oracle as LO  # noqa: E402
 from oracle import tiles_oracle as TO  # noqa: E402
 from oracle import tta_oracle as AO  # noqa: E402
@@ -394,8 +395,66 @@ def golden_losses():
     save("losses", **out)
 
 
+EXTRA_CASES = {
+    # name: (reference module factory, oracle function, input key, target key)
+    "softbce_default": (lambda: RL.SoftBCEWithLogitsLoss(), lambda z, t: LE.soft_bce_with_logits(z, t), "x", "t_ign"),
+    "softbce_smooth_sum": (lambda: RL.SoftBCEWithLogitsLoss(smooth_factor=0.1, reduction="sum"),
+                           lambda z, t: LE.soft_bce_with_logits(z, t, smooth_factor=0.1, reduction="sum"), "x", "t_ign"),
+    "softbce_weights": (lambda: RL.SoftBCEWithLogitsLoss(weight=torch.tensor([1.5, 0.7, 1.0]).view(3, 1, 1),
+                                                         pos_weight=torch.tensor([0.5, 2.0, 1.5]).view(3, 1, 1), ignore_index=None),
+                        lambda z, t: LE.soft_bce_with_logits(z, t, weight=torch.tensor([1.5, 0.7, 1.0]).view(3, 1, 1),
+                                                             pos_weight=torch.tensor([0.5, 2.0, 1.5]).view(3, 1, 1), ignore_index=None),
+                        "x", "t"),
+    "softbce_none": (lambda: RL.SoftBCEWithLogitsLoss(reduction="none", pos_weight=torch.tensor([3.0])),
+                     lambda z, t: LE.soft_bce_with_logits(z, t, reduction="none", pos_weight=torch.tensor([3.0])), "x", "t_ign"),
+    "balbce_default": (lambda: RL.BalancedBCEWithLogitsLoss(), lambda z, t: LE.balanced_bce_with_logits(z, t), "x", "t"),
+    "balbce_gamma_ignore": (lambda: RL.BalancedBCEWithLogitsLoss(gamma=0.7, ignore_index=-100),
+                            lambda z, t: LE.balanced_bce_with_logits(z, t, 0.7, -100), "x", "t_ign"),
+    "balbce_sum": (lambda: RL.BalancedBCEWithLogitsLoss(gamma=2.0, reduction="sum"),
+                   lambda z, t: LE.balanced_bce_with_logits(z, t, 2.0, None, "sum"), "x", "t"),
+    "qfl_mean": (lambda: RQ.QualityFocalLoss(), lambda z, t: LE.quality_focal_loss(z, t), "x", "t_soft"),
+    "qfl_sum_beta1p5": (lambda: RQ.QualityFocalLoss(beta=1.5, reduction="sum"), lambda z, t: LE.quality_focal_loss(z, t, 1.5, "sum"),
+                        "x", "t_soft"),
+    "qfl_normalized": (lambda: RQ.QualityFocalLoss(reduction="normalized"), lambda z, t: LE.quality_focal_loss(z, t, 2, "normalized"),
+                       "x", "t_soft"),
+    "qfl_none": (lambda: RQ.QualityFocalLoss(reduction="none"), lambda z, t: LE.quality_focal_loss(z, t, 2, "none"), "x", "t_soft"),
+    "bsf1": (lambda: RL.BinarySoftF1Loss(), lambda z, t: LE.binary_soft_f1(z, t), "x", "t"),
+    "bsf1_ignore": (lambda: RL.BinarySoftF1Loss(ignore_index=-100), lambda z, t: LE.binary_soft_f1(z, t, -100), "x", "t_ign"),
+    "sf1": (lambda: RL.SoftF1Loss(), lambda z, t: LE.soft_f1(z, t), "xc", "tc"),
+    "sf1_ignore0": (lambda: RL.SoftF1Loss(ignore_index=0), lambda z, t: LE.soft_f1(z, t, 0), "xc", "tc"),
+    "sf1_ignore7": (lambda: RL.SoftF1Loss(ignore_index=7), lambda z, t: LE.soft_f1(z, t, 7), "xc", "tc"),
+}
+
+
+def golden_losses_extra():
+    """SURVEY 8f rank 4 losses: reference outputs + gradients on seeded inputs; pins oracle/losses_extra_oracle.py."""
+    global RQ
+    from pytorch_toolbelt.losses import quality_focal_loss as RQ  # noqa: F811
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 16, 16, generator=g) * 3
+    t = (torch.rand(2, 3, 16, 16, generator=g) < 0.3).float()
+    t_ign = t.clone()
+    t_ign[torch.rand(2, 3, 16, 16, generator=g) < 0.08] = -100
+    t_soft = t * torch.rand(2, 3, 16, 16, generator=g)  # IoU-like quality targets in [0,1]
+    xc = torch.randn(41, 5, generator=g) * 2
+    tc = torch.randint(0, 5, (41,), generator=g)
+    data = dict(x=x, t=t, t_ign=t_ign, t_soft=t_soft, xc=xc, tc=tc)
+    out = {k: v.numpy() for k, v in data.items()}
+    for name, (ref_factory, orc, xk, tk) in EXTRA_CASES.items():
+        ref = ref_factory()
+        lr, gr = _grad(lambda z: ref(z, data[tk]), data[xk])
+        lo, go = _grad(lambda z: orc(z, data[tk]), data[xk])
+        assert torch.allclose(lr, lo, rtol=1e-6, atol=1e-8), (name, lr, lo)
+        assert torch.allclose(gr, go, rtol=1e-5, atol=1e-9), (name, (gr - go).abs().max())
+        out[f"{name}_loss"] = lr.numpy()
+        out[f"{name}_grad"] = gr.numpy()
+    save("losses_extra", **out)
+
+
 if __name__ == "__main__":
     golden_tiles()
     golden_tta()
     golden_losses()
+    golden_losses_extra()
     print("golden vectors written to", OUT)

@@ -29,7 +29,8 @@ class TB:
     BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = range(5)
     RED_NONE, RED_MEAN, RED_SUM, RED_GMEAN, RED_HMEAN, RED_HARMONIC1P, RED_LOGODD, RED_LOG1P = range(8)
     W_TABLE, W_ONES, W_PYRAMID, W_GAUSSIAN = range(4)
-    LOSS_NONE, LOSS_MEAN, LOSS_SUM, LOSS_BATCHWISE = range(4)
+    LOSS_NONE, LOSS_MEAN, LOSS_SUM, LOSS_BATCHWISE, LOSS_NORMALIZED = range(5)
+    EL_SOFT_BCE, EL_BALANCED_BCE, EL_QFL = 0, 1, 2
     PRE_NONE, PRE_SIGMOID = 0, 1
     OUT_LOGITS, OUT_ARGMAX, OUT_MASK = 0, 1, 2
     T_DENSE_F32, T_LABELS_I64 = 0, 1
@@ -119,6 +120,12 @@ class FocalParams(C.Structure):
     ]
 
 
+class ElemLossParams(C.Structure):
+    _fields_ = [("kind", C.c_int), ("reduction", C.c_int), ("smooth", C.c_float), ("has_smooth", C.c_int),
+                ("ignore_index", C.c_float), ("has_ignore", C.c_int), ("weight_n", C.c_int), ("pos_weight_n", C.c_int),
+                ("gamma", C.c_float), ("beta", C.c_float)]
+
+
 class DiceParams(C.Structure):
     _fields_ = [
         ("jaccard", C.c_int),
@@ -189,8 +196,9 @@ SIGNATURES = {
     ),
     "tb_wing_fwd_bwd": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "tb_scale_by_device_scalar": (_i, [_vp, _i64, _vp, _vp]),
-    "tb_lovasz_sorted": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
-    "tb_lovasz_workspace_bytes": (_sz, [_i64, _i]),
+    "tb_elem_loss_fwd_bwd": (_i, [_vp, _vp, _i64, _i, _i64, C.POINTER(ElemLossParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tb_soft_f1_workspace_bytes": (_sz, [_i64, _i]),
+    "tb_soft_f1_fwd_bwd": (_i, [_vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "tb_lovasz_fused_workspace_bytes": (_sz, [_i64, _i, _i64, _i]),
     "tb_lovasz_fwd_bwd": (_i, [_vp, _vp, _i, _i64, _i, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "tb_standin_model": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

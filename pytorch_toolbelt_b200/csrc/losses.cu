@@ -1,4 +1,4 @@
-// Segmentation-loss kernels for sm_100a: focal (sigmoid / softmax), dice / jaccard, wing, Lovasz.
+// Segmentation-loss kernels for sm_100a: focal (sigmoid / softmax), dice / jaccard, wing.
 //
 // Every loss is a streaming pass over the logits that produces the loss value AND the gradient w.r.t. the
 // logits in the same read of (x, target): HBM-bound, 128-bit loads/stores, grid of 8 CTAs per SM looping
@@ -11,98 +11,13 @@
 //   functional.py:188-247  soft_jaccard_score / soft_dice_score, dice.py:59-131, jaccard.py:48-103
 //                                                            -> region_stats_* / region_grad_* kernels
 //   functional.py:250-277  wing_loss                         -> wing_kernel
-//   lovasz.py:23-72,112-140 lovasz_grad + dot                -> lovasz_* kernels
+//   (Lovasz: csrc/lovasz.cu)
 #include <math.h>
 
 #include "common.cuh"
+#include "loss_common.cuh"
 
 namespace tb {
-
-constexpr int kLT = 256;  // threads per CTA for loss kernels
-
-static inline int loss_grid(long long work_items) {
-  const long long want = (work_items + kLT - 1) / kLT;
-  const long long cap = (long long)sm_count() * 8;
-  return (int)std::max<long long>(1, std::min<long long>(want, cap));
-}
-
-// ---- block reduction of N doubles; result valid in thread 0 -------------------------------------
-template <int N>
-__device__ __forceinline__ void block_reduce(double (&v)[N]) {
-  __shared__ double sh[N][kLT / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int n = 0; n < N; ++n) {
-    double x = v[n];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) sh[n][warp] = x;
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      double x = lane < kLT / 32 ? sh[n][lane] : 0.0;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      v[n] = x;
-    }
-  }
-  __syncthreads();
-}
-
-// sum `count` partial rows of N doubles (row stride N) in a fixed order: deterministic
-template <int N>
-__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int count, double (&out)[N]) {
-  double v[N];
-#pragma unroll
-  for (int n = 0; n < N; ++n) v[n] = 0.0;
-  for (int i = threadIdx.x; i < count; i += kLT) {
-#pragma unroll
-    for (int n = 0; n < N; ++n) v[n] += part[(size_t)i * N + n];
-  }
-  block_reduce<N>(v);
-#pragma unroll
-  for (int n = 0; n < N; ++n) out[n] = v[n];
-}
-
-template <int VW>
-__device__ __forceinline__ void ld_vec(const float* p, long long v, float (&o)[VW]) {
-  if (VW == 4) {
-    const float4 q = __ldcs(reinterpret_cast<const float4*>(p) + v);
-    o[0] = q.x; o[1 % VW] = q.y; o[2 % VW] = q.z; o[3 % VW] = q.w;
-  } else {
-    o[0] = __ldcs(p + v);
-  }
-}
-template <int VW>
-__device__ __forceinline__ void st_vec(float* p, long long v, const float (&o)[VW]) {
-  if (VW == 4)
-    __stcs(reinterpret_cast<float4*>(p) + v, make_float4(o[0], o[1 % VW], o[2 % VW], o[3 % VW]));
-  else
-    __stcs(p + v, o[0]);
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-// binary_cross_entropy_with_logits(x, t) = max(x,0) - x t + log1p(exp(-|x|))
-// log1p(e) for e = exp(-|x|) in (0,1]: one MUFU.LG2; absolute error ~4e-7, i.e. <= 1e-6 relative on any loss sum
-__device__ __forceinline__ float softplus_from_exp(float e) { return __logf(1.f + e); }
-__device__ __forceinline__ float bce_logits(float x, float t) {
-  return fmaxf(x, 0.f) - x * t + softplus_from_exp(__expf(-fabsf(x)));
-}
-__device__ __forceinline__ float powg(float base, float gamma) {
-  if (gamma == 2.f) return base * base;
-  if (gamma == 1.f) return base;
-  if (gamma == 0.f) return 1.f;
-  return powf(base, gamma);
-}
-// d/dbase base^gamma with torch's convention (0 for gamma == 0)
-__device__ __forceinline__ float dpowg(float base, float gamma) {
-  if (gamma == 2.f) return 2.f * base;
-  if (gamma == 1.f) return 1.f;
-  if (gamma == 0.f) return 0.f;
-  return gamma * powf(base, gamma - 1.f);
-}
 
 // =================================================================================================
 // sigmoid focal
@@ -985,112 +900,6 @@ __global__ void __launch_bounds__(kLT) scalar_finalize_kernel(const double* part
   if (threadIdx.x == 0 && loss_out) *loss_out = (float)(s[0] * scale);
 }
 
-// =================================================================================================
-// Lovasz on sorted errors: inclusive count scan -> Jaccard increments -> dot
-// =================================================================================================
-constexpr int kScanItems = 8;                 // elements per thread
-constexpr int kScanTile = kLT * kScanItems;   // elements per CTA
-
-struct LovaszArgs {
-  const float* err;
-  const float* gt;
-  long long begin, end;  // segment [begin,end)
-  int relu;
-  unsigned* tile_counts;  // [tiles] positives per tile, then exclusive-scanned in place
-  unsigned* total;        // [1]
-  float* grad;
-  double* partials;       // [tiles]
-};
-
-__global__ void __launch_bounds__(kLT) lovasz_count_kernel(LovaszArgs a) {
-  const long long base = a.begin + (long long)blockIdx.x * kScanTile;
-  double cnt[1] = {0.0};
-  for (int k = 0; k < kScanItems; ++k) {
-    const long long i = base + (long long)k * kLT + threadIdx.x;
-    if (i < a.end) cnt[0] += (a.gt[i] != 0.f) ? 1.0 : 0.0;
-  }
-  block_reduce<1>(cnt);
-  if (threadIdx.x == 0) a.tile_counts[blockIdx.x] = (unsigned)cnt[0];
-}
-
-// single CTA: exclusive scan of the tile counts (sequential over chunks of kLT; tiles <= a few 10k)
-__global__ void __launch_bounds__(kLT) lovasz_scan_tiles_kernel(unsigned* tile_counts, int tiles, unsigned* total) {
-  __shared__ unsigned sh[kLT];
-  __shared__ unsigned carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < tiles; base += kLT) {
-    const int i = base + threadIdx.x;
-    const unsigned v = i < tiles ? tile_counts[i] : 0u;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kLT; o <<= 1) {  // Hillis-Steele inclusive scan
-      const unsigned add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
-      __syncthreads();
-      sh[threadIdx.x] += add;
-      __syncthreads();
-    }
-    if (i < tiles) tile_counts[i] = carry + sh[threadIdx.x] - v;  // exclusive
-    __syncthreads();
-    if (threadIdx.x == kLT - 1) carry += sh[kLT - 1];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
-__global__ void __launch_bounds__(kLT) lovasz_apply_kernel(LovaszArgs a) {
-  __shared__ unsigned sh[kLT];
-  const long long tile_base = a.begin + (long long)blockIdx.x * kScanTile;
-  // each thread owns kScanItems CONSECUTIVE elements so that the in-thread scan is sequential
-  const long long my_base = tile_base + (long long)threadIdx.x * kScanItems;
-  unsigned bits[kScanItems];
-  unsigned local = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const long long i = my_base + k;
-    bits[k] = (i < a.end && a.gt[i] != 0.f) ? 1u : 0u;
-    local += bits[k];
-  }
-  sh[threadIdx.x] = local;
-  __syncthreads();
-  for (int o = 1; o < kLT; o <<= 1) {
-    const unsigned add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
-    __syncthreads();
-    sh[threadIdx.x] += add;
-    __syncthreads();
-  }
-  unsigned run = a.tile_counts[blockIdx.x] + sh[threadIdx.x] - local;  // positives strictly before my first element
-  const float gts = (float)(*a.total);
-  double dot[1] = {0.0};
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const long long i = my_base + k;
-    if (i < a.end) {
-      const float pos = (float)(i - a.begin);  // elements before i in the segment
-      // lovasz.py:27-34 at index k (cum = inclusive cumsums) and at k-1
-      const float cum = (float)(run + bits[k]);
-      const float jac = 1.f - (gts - cum) / (gts + (pos + 1.f) - cum);
-      float g = jac;
-      if (i > a.begin) {
-        const float cum_p = (float)run;
-        const float jac_p = 1.f - (gts - cum_p) / (gts + pos - cum_p);
-        g = jac - jac_p;
-      }
-      float e = a.err[i];
-      float ge = g;
-      if (a.relu) {
-        ge = e > 0.f ? g : 0.f;
-        e = fmaxf(e, 0.f);
-      }
-      dot[0] += (double)e * (double)g;
-      if (a.grad) a.grad[i] = ge;
-      run += bits[k];
-    }
-  }
-  block_reduce<1>(dot);
-  if (threadIdx.x == 0) a.partials[blockIdx.x] = dot[0];
-}
-
 // data[i] *= *scale unless *scale == 1 (autograd hands the upstream gradient as a device scalar; no host sync)
 __global__ void __launch_bounds__(kLT) scale_by_device_scalar_kernel(float* data, long long n, const float* scale) {
   const float sc = __ldg(scale);
@@ -1406,42 +1215,6 @@ int tb_scale_by_device_scalar(float* data, int64_t n, const float* scale_dev, vo
   if (n == 0) return TB_OK;
   scale_by_device_scalar_kernel<<<loss_grid(n), kLT, 0, (cudaStream_t)stream>>>(data, n, scale_dev);
   TB_LAUNCH_CHECK("scale_by_device_scalar_kernel");
-  return TB_OK;
-}
-
-size_t tb_lovasz_workspace_bytes(int64_t total, int segs) {
-  const size_t tiles = (size_t)(total + kScanTile - 1) / kScanTile + (size_t)segs;
-  return align_up(tiles * (sizeof(unsigned) + sizeof(double)) + 64, 256) + 256;
-}
-
-int tb_lovasz_sorted(const float* err_sorted, const float* gt_sorted, const int64_t* seg_offsets_host, int segs, int relu,
-                     float* seg_loss, float* grad_sorted, void* ws, size_t ws_bytes, void* stream) {
-  TB_REQUIRE(err_sorted && gt_sorted && seg_offsets_host && seg_loss && ws, TB_ERR_ARG, "tb_lovasz_sorted: null pointer");
-  TB_REQUIRE(segs > 0, TB_ERR_ARG, "tb_lovasz_sorted: segs must be positive");
-  const long long total = seg_offsets_host[segs] - seg_offsets_host[0];
-  TB_REQUIRE(total >= 0, TB_ERR_ARG, "tb_lovasz_sorted: bad offsets");
-  TB_REQUIRE(ws_bytes >= tb_lovasz_workspace_bytes(total, segs), TB_ERR_WORKSPACE, "tb_lovasz_sorted: workspace too small");
-  cudaStream_t s = (cudaStream_t)stream;
-  unsigned char* base = static_cast<unsigned char*>(ws);
-  for (int g = 0; g < segs; ++g) {
-    const long long b = seg_offsets_host[g], e = seg_offsets_host[g + 1];
-    TB_REQUIRE(e >= b, TB_ERR_ARG, "tb_lovasz_sorted: offsets must be non-decreasing");
-    if (e == b) {
-      TB_CUDA(cudaMemsetAsync(seg_loss + g, 0, sizeof(float), s));
-      continue;
-    }
-    const int tiles = (int)((e - b + kScanTile - 1) / kScanTile);
-    LovaszArgs a;
-    a.err = err_sorted; a.gt = gt_sorted; a.begin = b; a.end = e; a.relu = relu; a.grad = grad_sorted;
-    a.partials = reinterpret_cast<double*>(base);
-    a.tile_counts = reinterpret_cast<unsigned*>(base + align_up((size_t)tiles * sizeof(double), 16));
-    a.total = a.tile_counts + tiles;
-    lovasz_count_kernel<<<tiles, kLT, 0, s>>>(a);
-    lovasz_scan_tiles_kernel<<<1, kLT, 0, s>>>(a.tile_counts, tiles, a.total);
-    lovasz_apply_kernel<<<tiles, kLT, 0, s>>>(a);
-    scalar_finalize_kernel<<<1, kLT, 0, s>>>(a.partials, tiles, 1.0, seg_loss + g);
-  }
-  TB_LAUNCH_CHECK("lovasz kernels");
   return TB_OK;
 }
 

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kRT) lovasz_apply_kernel2(LovaszArgs2 a) {
   const uint32_t incl = block_scan_incl(local, &tile_total);  // (its barriers also publish sh_w)
   unsigned run = a.tile_counts[(size_t)seg * a.TA + blockIdx.x] + incl - local;  // positives strictly before my first element
   const float w = sh_w;
-  const float gts = (float)a.n_fg[seg];
+  const long long gts = (long long)a.n_fg[seg];
   double dot = 0.0;
 #pragma unroll
   for (int k = 0; k < kLovItems; ++k) {
@@ -342,14 +342,13 @@ __global__ void __launch_bounds__(kRT) lovasz_apply_kernel2(LovaszArgs2 a) {
     float gx = 0.f;
     if (i < n) {
       const unsigned bit = pp[k] >> 31;
-      // lovasz.py:27-34 at sorted position i (inclusive cumsums) minus the value at i-1
-      const float pos = (float)i;
-      const float cum = (float)(run + bit);
-      float gk = 1.f - (gts - cum) / (gts + (pos + 1.f) - cum);
-      if (i > 0) {
-        const float cum_p = (float)run;
-        gk -= 1.f - (gts - cum_p) / (gts + pos - cum_p);
-      }
+      // lovasz.py:27-34 at sorted position i (inclusive cumsums) minus the value at i-1. Intersection and union are exact
+      // integers converted to float ONCE, with the same expression for "the value at i-1" here and "the value at i" of the
+      // previous position, so the increments telescope exactly even beyond 2^24 elements (a float position counter does not:
+      // (float)(i-1) + 1 != (float)i there, and the error accumulates over the whole segment)
+      const long long cum = (long long)run + bit;
+      float gk = 1.f - (float)(gts - cum) / (float)(gts + (i + 1) - cum);
+      if (i > 0) gk -= 1.f - (float)(gts - (long long)run) / (float)(gts + i - (long long)run);
       run += bit;
       const float e = key_to_float(kk[k]);
       if (a.mode == 0) {

@@ -1,8 +1,10 @@
-"""bench.py body for N > 1 GPUs (one process per GPU, NCCL): strong scaling of ONE image over strips of tile rows.
+"""bench.py body for N > 1 GPUs (one process per GPU): strong scaling of ONE image over ragged strips.
 
-Every rank slices / predicts / merges only its own tile rows; the only cross-rank traffic is the (T-S)-row halo of
-un-normalised sums to the next strip (distributed/strips.py). The result stays sharded: rank g holds the final
-[K, rows_g, W] strip. value = image megapixels / max-over-ranks device time per step.
+Every rank slices / predicts / merges only its own row-major tile range (distributed/ragged.py); the only cross-rank traffic
+is the un-normalised partial sums of the canvas blocks that straddle a range boundary, stored by the merge kernel straight
+into the next rank's seed buffer over NVLink (CUDA-IPC mapped peer memory) and ordered by two flags per boundary. NCCL is
+used for the benchmark's own barriers / max-over-ranks reduction only, never on the data path. The result stays sharded:
+rank g holds the pixels whose last covering tile it owns. value = image megapixels / max-over-ranks device time per step.
 """
 from __future__ import annotations
 
@@ -17,10 +19,10 @@ import torch.distributed as dist
 from .. import _native as N
 from ..inference.engine import TiledInferenceEngine
 from ..utils.clocks import ClockSampler
-from .strips import StripMerger, StripPlan, partition_tile_rows
+from .ragged import RaggedMerger, RaggedPlan, partition_tiles
 
 
-def run_multi_gpu(args, CFG, METRIC, UNIT):
+def run_multi_gpu(args, CFG, cfg_name, METRIC, UNIT, WORKLOAD):
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -30,45 +32,44 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
 
     H, W, Cin, T, S, K = (CFG[k] for k in ("H", "W", "Cin", "T", "S", "K"))
     rng = np.random.default_rng(0)
-    image_host = torch.from_numpy(rng.integers(0, 256, (H, W, Cin)).astype(np.uint8)).pin_memory()
-    eng = TiledInferenceEngine((H, W, Cin), T, S, channels=K, weight=CFG["weight"], tta=CFG["tta"], device=dev)
+    image_np = rng.integers(0, 256, (H, W, Cin)).astype(np.uint8)
+    eng = TiledInferenceEngine((H, W, Cin), T, S, channels=K, weight=CFG["weight"], tta=CFG["tta"], analytic_weight=CFG["analytic"],
+                               device=dev)
     ny, nx = eng.slicer.grid_shape
     hp, wp = eng.slicer.target_shape
-    plan = StripPlan.build(ny, T, S, hp, rank, world)
+    top = eng.slicer.margin_top
+    plan = RaggedPlan.build(nx, ny, T, T, S, S, hp, rank, world)
     A = eng.views
-    t0, t1 = plan.r0 * nx, plan.r1 * nx
+    t0, t1 = plan.t0, plan.t1
     n_own = t1 - t0
     Wm = torch.randn(K, Cin, generator=torch.Generator().manual_seed(0))
     wm = (C.c_float * (K * Cin))(*[float(v) for v in Wm.flatten().tolist()])
-    stream = N.stream_ptr(dev)
 
     def model(x, out=None):
         y = out if out is not None else torch.empty((x.shape[0], K, T, T), dtype=torch.float32, device=dev)
         if x.shape[0]:
-            N.check(N.lib().tb_standin_model(x.data_ptr(), x.shape[0], Cin, K, T, T, wm, y.data_ptr(), stream), "standin")
+            N.check(N.lib().tb_standin_model(x.data_ptr(), x.shape[0], Cin, K, T, T, wm, y.data_ptr(), N.stream_ptr(dev)), "standin")
         return y
 
-    image = image_host.to(dev)
+    # the image rows this rank's tiles read (its slab): only those are uploaded in the e2e leg
+    iy0, iy1 = max(plan.rows[0] - top, 0), min(plan.rows[1] - top, H)
+    image_host = torch.from_numpy(image_np).pin_memory()
+    image = torch.zeros((H, W, Cin), dtype=torch.uint8, device=dev)
+    image[iy0:iy1].copy_(image_host[iy0:iy1])
+    del image_np
     aug = torch.empty((A * n_own, Cin, T, T), dtype=torch.float32, device=dev)
     pred = torch.empty((A * n_own, K, T, T), dtype=torch.float32, device=dev)
-    out = torch.empty((K, H, W), dtype=torch.float32, device=dev)  # only this rank's rows are ever written
-    if n_own:
-        eng.slice(image, t0, t1, out=aug)
-        model(aug, out=pred)
+    out = torch.empty((K, H, W), dtype=torch.float32, device=dev)  # only the pixels this rank owns are ever written
+    slicer = eng.slice_plan(image, t0, t1, out=aug)
+    slicer.run()
+    model(aug, out=pred)
     torch.cuda.synchronize()
-
-    # steady-state serving loop: every launch is marshalled once (PreparedLaunch), a step is 4 ctypes calls + 1 NCCL batch
-    def band_plan(rows, raw=False, init=None):
-        return eng.merge_plan(pred, out=None if raw else out, rows=rows, tile_rows=(plan.r0, plan.r1), raw=raw, init=init)
-
-    merger = StripMerger(band_plan, plan, K, wp, dev)
-    slicer = eng.slice_plan(image, t0, t1, out=aug) if n_own else None
+    merger = RaggedMerger(eng, plan, pred, out)
 
     def step(with_model=False):
-        if n_own:
-            slicer.run()
-            if with_model:
-                model(aug, out=pred)
+        slicer.run()
+        if with_model:
+            model(aug, out=pred)
         merger.run()
 
     def timed(fn, steps):
@@ -88,9 +89,10 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(True)
-    # clocks of rank 0's GPU during the timed region (every rank runs the same kernels on the same kind of GPU)
     with ClockSampler(local, uuid=str(getattr(torch.cuda.get_device_properties(dev), "uuid", "")) or None) as clocks:
         ms_step = timed(step, args.steps)
+        ms_slice = timed(slicer.run, args.steps)
+        ms_merge = timed(merger.run, args.steps)
         ms_with_model = timed(lambda: step(True), args.steps)
         extra = 0
         while extra < 200:  # same load, untimed, until the sampler has 3 readings (all ranks take the same decision)
@@ -102,49 +104,65 @@ def run_multi_gpu(args, CFG, METRIC, UNIT):
                 step()
             extra += 10
     clk = clocks.summary()
+    merger.check()
 
-    # e2e through the public API with host buffers: every rank uploads the image, runs its strip, downloads its rows
-    top = eng.slicer.margin_top
-    oy0, oy1 = max(plan.y0 - top, 0), min(plan.y1 - top, H)
-    rows_out = max(oy1 - oy0, 0) if not plan.empty else 0
+    # e2e through the public API with host buffers: every rank uploads ITS image slab, runs its tile range, downloads the
+    # rows its pixels lie in (the seam rows are downloaded by both neighbours; each holds its own pixels of them)
+    oy0, oy1 = iy0, iy1
+    rows_out = max(oy1 - oy0, 0)
     out_host = torch.empty((K, max(rows_out, 1), W), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        img = image_host.to(dev, non_blocking=True)
-        if n_own:
-            eng.slice(img, t0, t1, out=aug)
-            model(aug, out=pred)
+        image[iy0:iy1].copy_(image_host[iy0:iy1], non_blocking=True)
+        slicer.run()
+        model(aug, out=pred)
         merger.run()
         if rows_out:
             out_host[:, :rows_out].copy_(out[:, oy0:oy1], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
 
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, max(2, args.steps // 2))
+    merger.check()
 
+    slab = torch.tensor([float((iy1 - iy0) * W * Cin), float(K * rows_out * W * 4)], device=dev, dtype=torch.float64)
+    dist.all_reduce(slab)
     if rank == 0:
         mp = H * W / 1e6
+        peak = 6650.0
+        pk = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peak = float(json.load(open(pk))["hbm_gbs"])
+        n = eng.num_tiles
+        b_alg = H * W * Cin + n * A * Cin * T * T * 4 + n * A * K * T * T * 4 + K * H * W * 4
         halo_bytes = (K + 1) * (T - S) * wp * 4
+        parts = partition_tiles(n, world)
         line = {
             "metric": METRIC, "value": mp / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"cfg2: one 5000x5000x3 u8 image, 361 tiles 512/256, d4 TTA, K=4, pyramid; {ny} tile rows "
-                            f"split over {world} ranks as {[b - a for a, b in partition_tile_rows(ny, world)]}; "
-                            "engine-only (stand-in model excluded, predictions resident)",
+                "workload": WORKLOAD + f"; {n} tiles in row-major ranges of {sorted({b - a for a, b in parts}, reverse=True)} tiles over "
+                            f"{world} ranks; engine-only (stand-in model excluded, predictions resident)",
                 "l2": "per-rank inputs >> 126 MB L2; no flush needed",
-                "parallelism": f"strips{world}",
+                "parallelism": f"ragged-strips{world}",
                 "halo_bytes_per_boundary": halo_bytes,
-                "collective": "one NCCL send/recv of the un-normalised (K+1)x(T-S)xWp halo per strip boundary",
+                "collective": "none on the data path: the merge kernel stores the un-normalised (K+1) x (T-S) x Wp overlap sums of each range "
+                              "boundary into the next rank's seed buffer (NVLink peer stores, CUDA IPC) + 2 flags per boundary",
             },
             "with_model": {"value": mp / (ms_with_model * 1e-3), "unit": UNIT, "ms_per_step": ms_with_model},
+            "phases_ms_max_over_ranks": {"slice": ms_slice, "merge_with_exchange": ms_merge},
             "e2e": {"value": mp / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": H * W * Cin * world, "d2h_bytes_per_step": K * H * W * 4,
-                    "api": "per rank: pinned host image -> TiledInferenceEngine.slice/merge on its strip -> pinned host strip"},
-            "gpu_launches": (1 + 3) * args.steps,
+                    "h2d_bytes_per_step": int(slab[0].item()), "d2h_bytes_per_step": int(slab[1].item()),
+                    "api": "per rank: pinned host image SLAB -> slice / model / RaggedMerger on its tile range -> pinned host rows"},
+            "gpu_launches": (1 + 3 + 4) * args.steps,
+            "roofline_step": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_step * 1e-3) / 1e9, "peak": peak * world,
+                              "frac": b_alg / (ms_step * 1e-3) / 1e9 / (peak * world), "unit": "GB/s",
+                              "note": "whole-job algorithmic bytes / max-over-ranks step time / (N x measured single-GPU peak)"},
             "clocks": clk,
         }
         print(json.dumps(line))
     dist.barrier()
+    merger.close()
     dist.destroy_process_group()

@@ -211,7 +211,9 @@ class RaggedMerger:
             self.spill = tuple(launch(PH_SPILL, (plan.spill_y0, plan.spill_y0 + win), p) for p in (0, 1))
         self.final = tuple(launch(PH_FINAL, (y0, y1), p) for p in (0, 1))
         if plan.prev is not None:
-            self.seeded = tuple(launch(PH_SEEDED_FINAL | PH_SEEDED_SPILL, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
+            # (the last rank has nobody to spill to -- and no block of its range can need it)
+            seeded_mask = PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
+            self.seeded = tuple(launch(seeded_mask, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
 
     def run(self):
         """One step (epoch): [wait ack] spill -> [signal] final -> wait ready -> seeded [-> signal] -> ack."""

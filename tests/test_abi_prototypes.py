@@ -76,7 +76,7 @@ def _c_struct_fields(name):
 
 def test_mirror_structs_match_the_header():
     for cname, mirror in [("tb_weight", N.Weight), ("tb_grid", N.Grid), ("tb_focal_params", N.FocalParams),
-                          ("tb_dice_params", N.DiceParams), ("tb_merge_extra", N.MergeExtra), ("tb_peer_plan", N.PeerPlan)]:
+                          ("tb_dice_params", N.DiceParams), ("tb_merge_extra", N.MergeExtra), ("tb_peer_plan", N.PeerPlan), ("tb_elem_loss_params", N.ElemLossParams)]:
         want = _c_struct_fields(cname)
         got = [(f[0], _kind_of_ctypes(f[1])) for f in mirror._fields_]
         assert want == got, f"{cname}: header {want} vs ctypes {got}"
