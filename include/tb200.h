@@ -292,6 +292,29 @@ TB_API int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_ba
                                    int raw, int top, int left, int H, int W, float* out_num, float* out_den,
                                    const tb_merge_extra* ex, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 3-D TILES  (reference inference/tiles_3d.py)
+ * Volumes are [D,H,W] (W fastest), tiles [d,h,w], origins int32 [n,3] = (z,y,x).
+ * ---------------------------------------------------------------------------------------------- */
+/* VolumeSlicer.split / iter_split (tiles_3d.py:106-133): constant-padded sub-volume gather in the native element type
+ * (elem_bytes 1/2/4/8; fill_bits = the padding value's bit pattern). zyx are origins in the UNPADDED volume frame
+ * (crop origin - pad_before; may be negative / overhang). out [n,d,h,w]. */
+TB_API int tb_volume_crop_tiles(const void* vol, int elem_bytes, int D, int H, int W, const int32_t* zyx, int n, int d, int h,
+                         int w, uint64_t fill_bits, void* out, void* stream);
+/* VolumeMerger.integrate_batch (tiles_3d.py:195-208): volume[:, roi] += tile * weight; norm[:, roi] += weight for the n
+ * tiles of batch f32 [n,K,d,h,w]; zyx in the padded frame; float reductions in memory (order-nondeterministic rounding,
+ * like any parallel scatter; tb_volume_merge_all is the deterministic form). */
+TB_API int tb_volume_integrate(const float* batch, const int32_t* zyx, int n, int K, int d, int h, int w, const float* weight,
+                        float* volume, float* norm, int Dp, int Hp, int Wp, void* stream);
+/* VolumeMerger.merge (tiles_3d.py:210-211): out = volume / norm (no eps), nvox = Dp*Hp*Wp. */
+TB_API int tb_volume_normalize(const float* volume, const float* norm, int K, int64_t nvox, float* out, void* stream);
+/* The whole loop integrate_batch(all tiles, crops order) -> merge -> crop_to_orignal_size, output-stationary: pred f32
+ * [nd*nh*nw, K, d, h, w] with tile (i,j,k) at index (i*nh + j)*nw + k and padded origin (i*sd, j*sh, k*sw) (tiles_3d.py:76-96);
+ * out f32 [K,D,H,W] = the [pd:pd+D, ph:ph+H, pw:pw+W] window of the merged padded volume. Deterministic; bit-identical to
+ * integrate_batch fed in crops order followed by merge. */
+TB_API int tb_volume_merge_all(const float* pred, const float* weight, int K, int d, int h, int w, int sd, int sh, int sw, int nd,
+                        int nh, int nw, int pd, int ph, int pw, int D, int H, int W, float* out, void* stream);
+
 /* ---- peer memory for the multi-GPU halo: the one place where the library owns device memory (cudaMalloc'ed so that it
  * can be exported with CUDA IPC; torch's caching allocator sub-allocates and cannot). One process per GPU; a rank
  * allocates its mailbox (seed buffers + flags), exports the 64-byte handle, the neighbour opens it and gets a pointer

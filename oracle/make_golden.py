@@ -426,6 +426,41 @@ EXTRA_CASES = {
 }
 
 
+from oracle.make_golden_inputs import VOLUME_CASES, volume_case_inputs  # noqa: E402
+
+
+def golden_tiles3d():
+    """3-D tiles: VolumeSlicer grid / split and VolumeMerger integrate+merge outputs of the reference; pins tiles3d_oracle."""
+    from pytorch_toolbelt.inference.tiles_3d import VolumeMerger, VolumeSlicer
+
+    from oracle import tiles3d_oracle as T3
+
+    out = {}
+    for ci, (shape, tile, step) in enumerate(VOLUME_CASES):
+        ref = VolumeSlicer(shape, tile, step)
+        grid = T3.volume_grid(shape, tile, step)
+        origins = np.array([[r.start for r in roi] for roi in ref.crops])
+        assert np.array_equal(origins, grid["origins"]) and np.array_equal(ref.target_shape, grid["target_shape"])
+        assert np.array_equal(ref.pad_before, grid["pad_before"]) and np.array_equal(ref.num_tiles, grid["num_tiles"])
+        d, h, w = (int(v) for v in ref.tile_size)
+        vol, weight, preds = volume_case_inputs(ci, shape, len(ref.crops), (d, h, w))
+        tiles_ref = ref.split(vol, value=7)
+        tiles_orc = T3.split(vol, grid, value=7)
+        assert all(np.array_equal(a, b) for a, b in zip(tiles_ref, tiles_orc))
+        preds_t = torch.from_numpy(preds)
+        merger = VolumeMerger(ref.target_shape, 2, weight)
+        for s0 in range(0, len(ref.crops), 3):
+            merger.integrate_batch(preds_t[s0 : s0 + 3], ref.crops[s0 : s0 + 3])
+        merged = merger.merge()[ref.orignal_mask_roi]
+        assert torch.equal(merged, T3.merge(preds_t, grid, weight, 2))
+        pick = sorted({0, len(tiles_ref) // 2, len(tiles_ref) - 1})
+        out.update({f"c{ci}_origins": origins, f"c{ci}_target": np.array(ref.target_shape), f"c{ci}_pad_before": ref.pad_before,
+                    f"c{ci}_tile_idx": np.array(pick), f"c{ci}_tiles": np.stack([tiles_ref[t] for t in pick]),
+                    f"c{ci}_tile_sums": np.array([float(np.asarray(t, dtype=np.float64).sum()) for t in tiles_ref]),
+                    f"c{ci}_merged": merged.numpy()})
+    save("tiles3d", **out)
+
+
 def golden_losses_extra():
     """SURVEY 8f rank 4 losses: reference outputs + gradients on seeded inputs; pins oracle/losses_extra_oracle.py."""
     global RQ
@@ -457,4 +492,5 @@ if __name__ == "__main__":
     golden_tta()
     golden_losses()
     golden_losses_extra()
+    golden_tiles3d()
     print("golden vectors written to", OUT)

@@ -173,6 +173,10 @@ SIGNATURES = {
         [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
          _i, _i, _vp, _vp, C.POINTER(MergeExtra), _vp],
     ),
+    "tb_volume_crop_tiles": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, C.c_uint64, _vp, _vp]),
+    "tb_volume_integrate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "tb_volume_normalize": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "tb_volume_merge_all": (_i, [_vp, _vp] + [_i] * 16 + [_vp, _vp]),
     "tb_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p)]),
     "tb_peer_free": (_i, [_vp]),
     "tb_peer_export": (_i, [_vp, _vp]),

@@ -31,56 +31,87 @@ __device__ __forceinline__ void ldcs4(const float* p, float v[4]) {
 // ---------------------------------------------------------------------------------------------------------------
 // merge
 // ---------------------------------------------------------------------------------------------------------------
-// UW = unit width in pixels (128: Tw and Sx multiples of 128; 32 otherwise). SEP: separable in-register gaussian.
+// UW = unit width in pixels (128: Tw and Sx multiples of 128; 32 otherwise).
+// WK = how the tile weight is obtained: 0 table (L2-resident), 1 separable in-register gaussian, 2 weight_at() per pixel.
 // PLAIN: mean / sum reduction and no pre-activation (one view: the value itself): no per-element switch.
 // gridDim.y > 1: one row pass per CTA (small problems: 4x the CTAs, a quarter of the dependent load rounds per CTA).
-template <int UW, bool SEP, bool PLAIN>
+//
+// The covering tiles of a unit are the same for all of its pixels (lattice geometry), so thread 0 lists them once per CTA
+// in shared memory -- base pointer of the tile's first plane, canvas origin -- in the reference's accumulation order; the
+// inner loop is then: address = base + k*plane + (y - ty)*Tw + (x - tx), no per-thread coverage test, no index arithmetic.
+constexpr int kSvMaxTiles = 16;  // covering tiles per unit the list holds (4x4); larger covering sets -> general kernels
+
+template <int UW, int WK, bool PLAIN>
 __global__ void __launch_bounds__(kSV, 3) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
                                                                   int nux, int ux0) {
   constexpr int LPR = UW / 4;        // lanes per unit row
   constexpr int RPP = kSV / LPR;     // rows per pass
   constexpr int PASSES = 32 / RPP;
-  __shared__ int sh[4];
+  __shared__ const float* s_base[kSvMaxTiles];
+  __shared__ int s_ty[kSvMaxTiles], s_tx[kSvMaxTiles];
+  __shared__ int s_nt, s_cls;
   const tb_grid& g = a.grid;
   const int uy = blockIdx.x / nux, ux = blockIdx.x - uy * nux;
   const int Y0 = a.y0 - (a.y0 % 32) + uy * 32;
   const int X0 = (ux0 + ux) * UW;
+  const size_t plane = (size_t)g.Th * g.Tw;
   if (threadIdx.x == 0) {
     int ra = (Y0 - g.Th + g.Sy) / g.Sy;
     if (Y0 - g.Th + 1 <= 0) ra = 0;
-    int rb = (Y0 + 31) / g.Sy;
-    sh[0] = max(ra, a.r0);
-    sh[1] = min(rb, min(g.ny, a.r1) - 1);
+    const int rb_all = min((Y0 + 31) / g.Sy, g.ny - 1);
     int ca = (X0 - g.Tw + g.Sx) / g.Sx;
     if (X0 - g.Tw + 1 <= 0) ca = 0;
-    sh[2] = ca;
-    sh[3] = min((X0 + UW - 1) / g.Sx, g.nx - 1);
+    const int cb = min((X0 + UW - 1) / g.Sx, g.nx - 1);
+    int cls = 0;
+    bool skip = false;
+    if (a.peer.phase_mask) {  // multi-GPU ragged strips: is this block ours, seeded, a spill? (all covering tiles count)
+      cls = peer_block_class(a.peer, g.nx, ra, rb_all, ca, cb);
+      skip = cls == 0;
+    }
+    int nt = 0;
+    if (!skip) {
+      const int r_lo = max(ra, a.r0), r_hi = min(rb_all, a.r1 - 1);
+      for (int r = r_lo; r <= r_hi; ++r)
+        for (int c = ca; c <= cb; ++c) {
+          const int rel = r * g.nx + c - a.first_tile;
+          if (rel < 0 || rel >= a.covered_tiles) continue;  // tile not resident (band mode / ragged strips)
+          int bi = 0, pos = rel;
+          if (a.batch_tiles < a.covered_tiles) {
+            bi = rel / a.batch_tiles;
+            pos = rel - bi * a.batch_tiles;
+          }
+          if (nt < kSvMaxTiles) {
+            s_base[nt] = ptrs.p[bi] + (size_t)pos * a.K * plane;
+            s_ty[nt] = r * g.Sy;
+            s_tx[nt] = c * g.Sx;
+          }
+          ++nt;
+        }
+    }
+    s_nt = skip ? -1 : nt;
+    s_cls = cls;
   }
   __syncthreads();
-  const int ra = sh[0], rb = sh[1], ca = sh[2], cb = sh[3];
-  int cls = 0;
-  if (a.peer.phase_mask) {  // multi-GPU ragged strips: is this block ours, seeded, a spill? (uniform over the CTA)
-    cls = peer_block_class(a.peer, g.nx, ra, rb, ca, cb);
-    if (!cls) return;
-  }
+  const int nt = s_nt, cls = s_cls;
+  if (nt < 0) return;
   const bool seeded = cls & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), spill = cls & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
   const int lc = threadIdx.x % LPR, row0 = threadIdx.x / LPR;
   const int x = X0 + 4 * lc;
   if (x >= a.Wp) return;  // (after the only barrier)
   const int rows = a.y1 - a.y0;
-  const size_t plane = (size_t)g.Th * g.Tw;
-  const bool one_batch = a.batch_tiles >= a.covered_tiles;
 
-  // separable gaussian: w(i,j) = exp(-di^2 c) * exp(-dj^2 c); the column factors of the (<= 2) covering tile columns
-  // live in registers (selected by compare, never indexed: a runtime index would push the array to local memory)
-  float wj0[4] = {0.f, 0.f, 0.f, 0.f}, wj1[4] = {0.f, 0.f, 0.f, 0.f};
-  if (SEP) {
+  // separable gaussian: w(i,j) = exp(-di^2 c) * exp(-dj^2 c); the column factors of the first four listed tiles live in
+  // registers (static indexing only: a runtime index would push the array to local memory)
+  float wj[4][4];
+  if (WK == 1) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float d0 = (float)(x - ca * g.Sx + e) - a.w.wc;
-      const float d1 = (float)(x - (ca + 1) * g.Sx + e) - a.w.wc;
-      wj0[e] = __expf(-(d0 * d0) * a.w.param);
-      wj1[e] = __expf(-(d1 * d1) * a.w.param);
+    for (int u = 0; u < 4; ++u) {
+      const int tx = u < nt ? s_tx[u] : 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float dj = (float)(x - tx + e) - a.w.wc;
+        wj[u][e] = __expf(-(dj * dj) * a.w.param);
+      }
     }
   }
 
@@ -91,6 +122,7 @@ __global__ void __launch_bounds__(kSV, 3) merge_single_view_kernel(MergeAllArgs 
     const int y = Y0 + row0 + p * RPP;
     if (y < a.y0 || y >= a.y1) continue;
     LabelState ls;
+#pragma unroll 1
     for (int k = 0; k < a.K; ++k) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
       if (a.init_num) {
@@ -105,47 +137,32 @@ __global__ void __launch_bounds__(kSV, 3) merge_single_view_kernel(MergeAllArgs 
         acc[0] = n4.x; acc[1] = n4.y; acc[2] = n4.z; acc[3] = n4.w;
         den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
-      int r = ra, c = ca;
-      while (r <= rb) {
+#pragma unroll 1
+      for (int u0 = 0; u0 < nt; u0 += 4) {  // (nt <= 4 almost always: one trip)
         float pv[4][4], wv[4][4];
-        bool ok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          ok[u] = false;
-          if (r <= rb) {
-            const int rel = r * g.nx + c - a.first_tile;
-            const int i = y - r * g.Sy, j = x - c * g.Sx;
-            if (rel >= 0 && rel < a.covered_tiles && i >= 0 && i < g.Th && j >= 0 && j + 3 < g.Tw) {
-              int bi = 0, pos = rel;
-              if (!one_batch) {
-                bi = rel / a.batch_tiles;
-                pos = rel - bi * a.batch_tiles;
-              }
-              ok[u] = true;
-              ldcs4(ptrs.p[bi] + ((size_t)pos * a.K + k) * plane + (size_t)i * g.Tw + j, pv[u]);
-              if (SEP) {
-                const float di = (float)i - a.w.hc;
-                const float wi = __expf(-(di * di) * a.w.param);
-                const bool first_col = (c == ca);  // <= 2 covering columns on this path (host checks)
+          if (u0 + u < nt) {
+            const int i = y - s_ty[u0 + u], j = x - s_tx[u0 + u];
+            const int off = i * g.Tw + j;
+            ldcs4(s_base[u0 + u] + (size_t)k * plane + off, pv[u]);
+            if (WK == 0) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + off));
+              wv[u][0] = w4.x; wv[u][1] = w4.y; wv[u][2] = w4.z; wv[u][3] = w4.w;
+            } else if (WK == 1) {
+              const float di = (float)i - a.w.hc;
+              const float wi = __expf(-(di * di) * a.w.param);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) wv[u][e] = wi * (first_col ? wj0[e] : wj1[e]);
-              } else if (a.w.kind == TB_W_TABLE) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + (size_t)i * g.Tw + j));
-                wv[u][0] = w4.x; wv[u][1] = w4.y; wv[u][2] = w4.z; wv[u][3] = w4.w;
-              } else {
+              for (int e = 0; e < 4; ++e) wv[u][e] = wi * wj[u][e];  // (WK == 1 is only launched with nt <= 4: u0 == 0)
+            } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) wv[u][e] = weight_at<float>(a.w, i, j + e);
-              }
-            }
-            if (++c > cb) {
-              c = ca;
-              ++r;
+              for (int e = 0; e < 4; ++e) wv[u][e] = weight_at<float>(a.w, i, j + e);
             }
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (ok[u]) {
+          if (u0 + u < nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float val = PLAIN ? pv[u][e]
@@ -184,8 +201,9 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   if (a.raw && (!al16(a.out_num) || !al16(a.out_den))) return cudaErrorNotSupported;
   const bool wide = (g.Tw % 128 == 0) && (g.Sx % 128 == 0);
   const int uw = wide ? 128 : 32;
-  const int cover_cols = (g.Tw + g.Sx - 1) / g.Sx;
-  const bool sep = a.w.kind == TB_W_GAUSSIAN && cover_cols <= 2;
+  const int cover = ((g.Tw + g.Sx - 1) / g.Sx) * ((g.Th + g.Sy - 1) / g.Sy);
+  if (cover > kSvMaxTiles) return cudaErrorNotSupported;
+  const int wk = a.w.kind == TB_W_TABLE ? 0 : ((a.w.kind == TB_W_GAUSSIAN && cover <= 4) ? 1 : 2);
   const bool plain = (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) && a.pre == TB_PRE_NONE;
   const int xa = a.raw ? 0 : a.left, xb = a.raw ? a.Wp : a.left + a.W;
   const int ux0 = xa / uw, nux = (xb + uw - 1) / uw - ux0;
@@ -193,16 +211,16 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   if (units <= 0 || units >= (1ll << 31)) return cudaErrorNotSupported;
   // few units (small images): one row pass per CTA, so that the grid still fills the GPU several times over
   const int passes = wide ? 4 : 1;
-  const bool split = passes > 1 && units < (long long)sm_count() * 4 * 8;
+  const bool split = passes > 1 && units < (long long)sm_count() * 3 * 8;
   const dim3 grid((unsigned)units, split ? passes : 1);
-#define TB_SV(UW, SEP_, PLAIN_) merge_single_view_kernel<UW, SEP_, PLAIN_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
+#define TB_SV(UW, WK_, PLAIN_) merge_single_view_kernel<UW, WK_, PLAIN_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
+#define TB_SV_WK(UW, PLAIN_) do { if (wk == 0) TB_SV(UW, 0, PLAIN_); else if (wk == 1) TB_SV(UW, 1, PLAIN_); else TB_SV(UW, 2, PLAIN_); } while (0)
   if (wide) {
-    if (sep) { if (plain) TB_SV(128, true, true); else TB_SV(128, true, false); }
-    else { if (plain) TB_SV(128, false, true); else TB_SV(128, false, false); }
+    if (plain) TB_SV_WK(128, true); else TB_SV_WK(128, false);
   } else {
-    if (sep) { if (plain) TB_SV(32, true, true); else TB_SV(32, true, false); }
-    else { if (plain) TB_SV(32, false, true); else TB_SV(32, false, false); }
+    if (plain) TB_SV_WK(32, true); else TB_SV_WK(32, false);
   }
+#undef TB_SV_WK
 #undef TB_SV
   return cudaGetLastError();
 }
@@ -219,7 +237,7 @@ constexpr int kRowsInFlight = 8;
 
 // grid (bands, n): a thread keeps a 4-pixel column group of the tile and walks down the band's rows kRowsInFlight at a time
 template <typename SrcT>
-__global__ void __launch_bounds__(kSV) slice_single_view_kernel(SliceArgs a) {
+__global__ void __launch_bounds__(kSV, 3) slice_single_view_kernel(SliceArgs a) {
   const int groups = a.Tw >> 2;            // host guarantees Tw % 4 == 0
   const int gpt = min(groups, kSV);        // column groups side by side
   const int rsub = threadIdx.x / gpt, rstep = kSV / gpt;
@@ -240,33 +258,54 @@ __global__ void __launch_bounds__(kSV) slice_single_view_kernel(SliceArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) sx[e] = border_remap(x0 + j + e, 0, a.W, a.border);
     const bool word_ok = tile_words && sx[0] >= 0 && sx[3] == sx[0] + 3;
-    for (int i0 = i_begin + rsub; i0 < i_end; i0 += kRowsInFlight * rstep) {
-      if (word_ok) {
-        uchar4 q[kRowsInFlight];
-        bool fill[kRowsInFlight];
+    if (word_ok) {
+      // software pipeline: the loads of batch n+1 are in flight while batch n is converted and stored (under a flood of
+      // streaming stores a load takes several microseconds to come back -- ncu: long-scoreboard stalls, 45 % DRAM)
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(img) + sx[0];
+      float* o_col = out_tile + j;
+      auto load_batch = [&](int ib, uchar4 (&q)[kRowsInFlight], unsigned& fillmask) {
+        fillmask = 0;
 #pragma unroll
         for (int m = 0; m < kRowsInFlight; ++m) {
-          const int i = i0 + m * rstep;
+          const int i = ib + m * rstep;
           const int sy = i < i_end ? border_remap(y0 + i, 0, a.H, a.border) : -1;
-          fill[m] = sy < 0;
           q[m] = make_uchar4(0, 0, 0, 0);
-          if (!fill[m])
-            q[m] = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(img) + (size_t)sy * a.W + sx[0]));
+          if (sy < 0) fillmask |= 1u << m;
+          else q[m] = __ldg(reinterpret_cast<const uchar4*>(src + (size_t)sy * a.W));
         }
+      };
+      auto store_batch = [&](int ib, const uchar4 (&q)[kRowsInFlight], unsigned fillmask) {
 #pragma unroll
         for (int m = 0; m < kRowsInFlight; ++m) {
-          const int i = i0 + m * rstep;
-          if (i >= i_end) break;
-          float v[4] = {(float)q[m].x, (float)q[m].y, (float)q[m].z, (float)q[m].w};
-          if (fill[m]) v[0] = v[1] = v[2] = v[3] = a.bval[0];
-          if (a.has_affine) {
+          const int i = ib + m * rstep;
+          if (i < i_end) {
+            float v[4] = {(float)q[m].x, (float)q[m].y, (float)q[m].z, (float)q[m].w};
+            if (fillmask & (1u << m)) v[0] = v[1] = v[2] = v[3] = a.bval[0];
+            if (a.has_affine) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[0]), a.bias[0]);
+              for (int e = 0; e < 4; ++e) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[0]), a.bias[0]);
+            }
+            __stcs(reinterpret_cast<float4*>(o_col + (size_t)i * a.Tw), make_float4(v[0], v[1], v[2], v[3]));
           }
-          __stcs(reinterpret_cast<float4*>(out_tile + (size_t)i * a.Tw + j), make_float4(v[0], v[1], v[2], v[3]));
         }
-        continue;
+      };
+      const int step = kRowsInFlight * rstep;
+      uchar4 qa[kRowsInFlight], qb[kRowsInFlight];
+      unsigned fa, fb;
+      int i0 = i_begin + rsub;
+      load_batch(i0, qa, fa);
+      while (i0 < i_end) {
+        load_batch(i0 + step, qb, fb);
+        store_batch(i0, qa, fa);
+        i0 += step;
+        if (i0 >= i_end) break;
+        load_batch(i0 + step, qa, fa);
+        store_batch(i0, qb, fb);
+        i0 += step;
       }
+      continue;
+    }
+    for (int i0 = i_begin + rsub; i0 < i_end; i0 += kRowsInFlight * rstep) {
       for (int m = 0; m < kRowsInFlight; ++m) {
         const int i = i0 + m * rstep;
         if (i >= i_end) break;
