@@ -292,6 +292,14 @@ TB_API int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_ba
                                    int raw, int top, int left, int H, int W, float* out_num, float* out_den,
                                    const tb_merge_extra* ex, void* stream);
 
+/* SURVEY 8f rank 2, model ensembles (inference/ensembling.py:71-123): out[i] = reduction over m of inputs[m][i] for M
+ * separately allocated f32 tensors of n elements (inputs_host: HOST array of M <= 64 device pointers). One pass, no [M,...]
+ * stack; reductions and summation order (m = 0..M-1) as in tb_tta_deaugment / _deaugment_averaging (tta.py:63-96). */
+TB_API int tb_stack_reduce(const float* const* inputs_host, int M, int64_t n, int reduction, float* out, void* stream);
+/* ApplySigmoidTo / ApplySoftmaxTo (inference/ensembling.py:12-68) in place on f32 [B,C,inner]:
+ * mode 0: x.mul(temperature).sigmoid_();  mode 1: x.mul(temperature).softmax(dim=1). */
+TB_API int tb_activation_inplace(float* x, int64_t B, int C, int64_t inner, int mode, float temperature, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3-D TILES  (reference inference/tiles_3d.py)
  * Volumes are [D,H,W] (W fastest), tiles [d,h,w], origins int32 [n,3] = (z,y,x).

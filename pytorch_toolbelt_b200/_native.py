@@ -173,6 +173,8 @@ SIGNATURES = {
         [_vp, _i, _i, _i, _i, C.POINTER(Grid), _i, _i, _i, C.POINTER(Weight), _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i,
          _i, _i, _vp, _vp, C.POINTER(MergeExtra), _vp],
     ),
+    "tb_stack_reduce": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "tb_activation_inplace": (_i, [_vp, _i64, _i, _i64, _i, _f, _vp]),
     "tb_volume_crop_tiles": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, C.c_uint64, _vp, _vp]),
     "tb_volume_integrate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "tb_volume_normalize": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),

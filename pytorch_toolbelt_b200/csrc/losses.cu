@@ -714,6 +714,21 @@ struct JointArgs {
 };
 
 // shared by both passes so that they see identical p / loss terms
+// FAST: the default BinaryFocalLoss() of BASELINE config 3 (gamma == 2, no alpha / class weights / ignore / reduced threshold):
+// closed forms, one ex2 + one rcp + one lg2 per element, no option branches. Same formulas as focal_elem, so the value
+// agrees with the general path to rounding (division by the MUFU reciprocal: <= 2 ulp on sigmoid).
+__device__ __forceinline__ void joint_elem_fast(float x, float t, float& pr, float& L, float& dL) {
+  const float e = __expf(-fabsf(x));
+  const float r = __fdividef(1.f, 1.f + e);
+  pr = x >= 0.f ? r : e * r;
+  const float ce = fmaxf(x, 0.f) - x * t + __logf(1.f + e);
+  const float base = pr + t - 2.f * pr * t;       // 1 - pt,  pt = p t + (1 - p)(1 - t)
+  const float focal = base * base;
+  const float dpt = pr * (1.f - pr) * (2.f * t - 1.f);
+  L = focal * ce;
+  dL = -2.f * base * dpt * ce + focal * (pr - t);
+}
+
 __device__ __forceinline__ void joint_elem(const JointArgs& a, float x, float t, int c, float& pr, float& L, float& dL) {
   const float ex = __expf(-fabsf(x));
   const float inv = 1.f / (1.f + ex);
@@ -722,7 +737,7 @@ __device__ __forceinline__ void joint_elem(const JointArgs& a, float x, float t,
   focal_elem(a.f, x, t, pr, pr * (1.f - pr), pr, softplus_from_exp(ex), c, L, F, dL, dF);
 }
 
-template <int VW>
+template <int VW, bool FAST>
 __global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
   const long long row = blockIdx.y;  // b*C + c
   const int c = (int)(row % a.C);
@@ -730,30 +745,37 @@ __global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
   const float* xr = a.x + row * a.inner;
   const float* tr = a.t + row * a.inner;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  float part[4] = {0.f, 0.f, 0.f, 0.f};  // float partials over a few vectors, flushed into the doubles every 4th trip
+  int trips = 0;
   for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < innerv; v += (long long)gridDim.x * kLT) {
     float xs[VW], ts[VW];
     ld_vec<VW>(xr, v, xs);
     ld_vec<VW>(tr, v, ts);
-    float I = 0.f, S = 0.f, T = 0.f, Ls = 0.f;
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
       float pr, L, dL;
-      joint_elem(a, xs[e], ts[e], c, pr, L, dL);
-      Ls += L;
+      if (FAST) joint_elem_fast(xs[e], ts[e], pr, L, dL);
+      else joint_elem(a, xs[e], ts[e], c, pr, L, dL);
+      part[3] += L;
       float t = ts[e];
-      if (a.d.has_ignore && t == a.d.ignore_index) {  // dice.py:85-88,107-111
+      if (!FAST && a.d.has_ignore && t == a.d.ignore_index) {  // dice.py:85-88,107-111
         pr = 0.f;
         t = 0.f;
       }
-      I += pr * t;
-      S += pr + t;
-      T += t;
+      part[0] += pr * t;
+      part[1] += pr + t;
+      part[2] += t;
     }
-    acc[0] += (double)I;
-    acc[1] += (double)S;
-    acc[2] += (double)T;
-    acc[3] += (double)Ls;
+    if ((++trips & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[q] += (double)part[q];
+        part[q] = 0.f;
+      }
+    }
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] += (double)part[q];
   block_reduce<4>(acc);
   if (threadIdx.x == 0) {
     double* o = a.partials + ((size_t)row * gridDim.x + blockIdx.x) * 4;
@@ -778,7 +800,7 @@ __global__ void __launch_bounds__(kLT) joint_finalize_kernel(const double* parti
   }
 }
 
-template <int VW>
+template <int VW, bool FAST>
 __global__ void __launch_bounds__(kLT) joint_grad_kernel(JointArgs a) {
   extern __shared__ float sh_coef[];  // [C][2]: w_dice * (alpha, beta) / number of averaged classes
   const int nsel = a.classes ? a.n_classes : a.C;
@@ -826,9 +848,10 @@ __global__ void __launch_bounds__(kLT) joint_grad_kernel(JointArgs a) {
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
       float pr, L, dL;
-      joint_elem(a, xs[e], ts[e], c, pr, L, dL);
+      if (FAST) joint_elem_fast(xs[e], ts[e], pr, L, dL);
+      else joint_elem(a, xs[e], ts[e], c, pr, L, dL);
       const float t = ts[e];
-      const bool ign = a.d.has_ignore && t == a.d.ignore_index;
+      const bool ign = !FAST && a.d.has_ignore && t == a.d.ignore_index;
       const float gd = ign ? 0.f : (al * t + be) * (pr * (1.f - pr));
       g[e] = fscale * dL + gd;
     }
@@ -1170,16 +1193,23 @@ int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int6
   a.partials = static_cast<double*>(ws);
   a.stats = a.partials + (size_t)B * C * chunks * 4;
   dim3 grid1(chunks, (unsigned)(B * C));
-  if (vec4)
-    joint_stats_kernel<4><<<grid1, kLT, 0, s>>>(a);
+  // the common configuration (BinaryFocalLoss() + DiceLoss / JaccardLoss without ignore_index) takes the branch-free kernels
+  const bool fast = vec4 && fp->gamma == 2.f && !fp->has_alpha && !class_w && !fp->has_ignore && !fp->has_reduced_threshold &&
+                    !dp->has_ignore;
+  if (fast)
+    joint_stats_kernel<4, true><<<grid1, kLT, 0, s>>>(a);
+  else if (vec4)
+    joint_stats_kernel<4, false><<<grid1, kLT, 0, s>>>(a);
   else
-    joint_stats_kernel<1><<<grid1, kLT, 0, s>>>(a);
+    joint_stats_kernel<1, false><<<grid1, kLT, 0, s>>>(a);
   joint_finalize_kernel<<<C, kLT, 0, s>>>(a.partials, B, C, chunks, a.stats);
   const int grid2 = grad ? loss_grid(B * C * inner / (vec4 ? 4 : 1)) : 1;
-  if (vec4)
-    joint_grad_kernel<4><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
+  if (fast)
+    joint_grad_kernel<4, true><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
+  else if (vec4)
+    joint_grad_kernel<4, false><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
   else
-    joint_grad_kernel<1><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
+    joint_grad_kernel<1, false><<<grid2, kLT, 2 * C * sizeof(float), s>>>(a);
   TB_LAUNCH_CHECK("joint_focal_dice_kernel");
   return TB_OK;
 }

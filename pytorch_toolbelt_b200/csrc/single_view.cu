@@ -15,6 +15,8 @@
 //           float4 stores); the grid is sized to >= 8 waves of resident CTAs so the tail wave costs little.
 //
 // Reference: inference/tiles.py:177-204 (split), :321-350,271-280 (integrate_batch + merge + crop).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "tiles_args.cuh"
@@ -237,7 +239,7 @@ constexpr int kRowsInFlight = 8;
 
 // grid (bands, n): a thread keeps a 4-pixel column group of the tile and walks down the band's rows kRowsInFlight at a time
 template <typename SrcT>
-__global__ void __launch_bounds__(kSV, 3) slice_single_view_kernel(SliceArgs a) {
+__global__ void __launch_bounds__(kSV) slice_single_view_kernel(SliceArgs a) {
   const int groups = a.Tw >> 2;            // host guarantees Tw % 4 == 0
   const int gpt = min(groups, kSV);        // column groups side by side
   const int rsub = threadIdx.x / gpt, rstep = kSV / gpt;
@@ -249,62 +251,11 @@ __global__ void __launch_bounds__(kSV, 3) slice_single_view_kernel(SliceArgs a) 
   const int rows_per_band = (a.Th + gridDim.x - 1) / gridDim.x;
   const int i_begin = blockIdx.x * rows_per_band, i_end = min(a.Th, i_begin + rows_per_band);
   float* out_tile = a.out + (size_t)t * a.C * plane;
-  // 4 consecutive bytes of one row as a single 32-bit load: u8, one channel, the 4-group inside the image and 4-aligned
-  const bool tile_words = sizeof(SrcT) == 1 && a.C == 1 && ((a.W & 3) == 0) && ((x0 & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(a.img) & 3) == 0);
   for (int cg = threadIdx.x % gpt; cg < groups; cg += gpt) {
     const int j = cg << 2;
     int sx[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) sx[e] = border_remap(x0 + j + e, 0, a.W, a.border);
-    const bool word_ok = tile_words && sx[0] >= 0 && sx[3] == sx[0] + 3;
-    if (word_ok) {
-      // software pipeline: the loads of batch n+1 are in flight while batch n is converted and stored (under a flood of
-      // streaming stores a load takes several microseconds to come back -- ncu: long-scoreboard stalls, 45 % DRAM)
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(img) + sx[0];
-      float* o_col = out_tile + j;
-      auto load_batch = [&](int ib, uchar4 (&q)[kRowsInFlight], unsigned& fillmask) {
-        fillmask = 0;
-#pragma unroll
-        for (int m = 0; m < kRowsInFlight; ++m) {
-          const int i = ib + m * rstep;
-          const int sy = i < i_end ? border_remap(y0 + i, 0, a.H, a.border) : -1;
-          q[m] = make_uchar4(0, 0, 0, 0);
-          if (sy < 0) fillmask |= 1u << m;
-          else q[m] = __ldg(reinterpret_cast<const uchar4*>(src + (size_t)sy * a.W));
-        }
-      };
-      auto store_batch = [&](int ib, const uchar4 (&q)[kRowsInFlight], unsigned fillmask) {
-#pragma unroll
-        for (int m = 0; m < kRowsInFlight; ++m) {
-          const int i = ib + m * rstep;
-          if (i < i_end) {
-            float v[4] = {(float)q[m].x, (float)q[m].y, (float)q[m].z, (float)q[m].w};
-            if (fillmask & (1u << m)) v[0] = v[1] = v[2] = v[3] = a.bval[0];
-            if (a.has_affine) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[0]), a.bias[0]);
-            }
-            __stcs(reinterpret_cast<float4*>(o_col + (size_t)i * a.Tw), make_float4(v[0], v[1], v[2], v[3]));
-          }
-        }
-      };
-      const int step = kRowsInFlight * rstep;
-      uchar4 qa[kRowsInFlight], qb[kRowsInFlight];
-      unsigned fa, fb;
-      int i0 = i_begin + rsub;
-      load_batch(i0, qa, fa);
-      while (i0 < i_end) {
-        load_batch(i0 + step, qb, fb);
-        store_batch(i0, qa, fa);
-        i0 += step;
-        if (i0 >= i_end) break;
-        load_batch(i0 + step, qa, fa);
-        store_batch(i0, qb, fb);
-        i0 += step;
-      }
-      continue;
-    }
     for (int i0 = i_begin + rsub; i0 < i_end; i0 += kRowsInFlight * rstep) {
       for (int m = 0; m < kRowsInFlight; ++m) {
         const int i = i0 + m * rstep;
@@ -330,6 +281,99 @@ __global__ void __launch_bounds__(kSV, 3) slice_single_view_kernel(SliceArgs a) 
   }
 }
 
+// u8, one channel (cfg 5): 4 pixels = one 32-bit load -> one streaming float4 store. RIF rows in flight per thread; PIPE: the
+// loads of batch n+1 are issued before batch n is stored; MINB: resident CTAs per SM the register budget is cut for.
+template <int RIF, bool PIPE, int MINB>
+__global__ void __launch_bounds__(kSV, MINB) slice_u8c1_kernel(SliceArgs a) {
+  const int groups = a.Tw >> 2;
+  const int gpt = min(groups, kSV);
+  const int rsub = threadIdx.x / gpt, rstep = kSV / gpt;
+  if (rsub >= rstep) return;
+  const int t = blockIdx.y;
+  const unsigned char* img = static_cast<const unsigned char*>(a.img);
+  const int x0 = __ldg(a.xy + 2 * t), y0 = __ldg(a.xy + 2 * t + 1);
+  const int rows_per_band = (a.Th + gridDim.x - 1) / gridDim.x;
+  const int i_begin = blockIdx.x * rows_per_band, i_end = min(a.Th, i_begin + rows_per_band);
+  float* out_tile = a.out + (size_t)t * a.Th * a.Tw;
+  const bool tile_words = ((a.W & 3) == 0) && ((x0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.img) & 3) == 0);
+  const int step = RIF * rstep;
+  for (int cg = threadIdx.x % gpt; cg < groups; cg += gpt) {
+    const int j = cg << 2;
+    int sx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sx[e] = border_remap(x0 + j + e, 0, a.W, a.border);
+    const bool word_ok = tile_words && sx[0] >= 0 && sx[3] == sx[0] + 3;
+    float* o_col = out_tile + j;
+    auto load_batch = [&](int ib, uchar4 (&q)[RIF], unsigned& fillmask) {
+      fillmask = 0;
+#pragma unroll
+      for (int m = 0; m < RIF; ++m) {
+        const int i = ib + m * rstep;
+        const int sy = i < i_end ? border_remap(y0 + i, 0, a.H, a.border) : -1;
+        q[m] = make_uchar4(0, 0, 0, 0);
+        if (sy < 0) {
+          fillmask |= 1u << m;
+        } else if (word_ok) {
+          q[m] = __ldg(reinterpret_cast<const uchar4*>(img + (size_t)sy * a.W + sx[0]));
+        } else {  // tile column not 4-aligned in the image, or the 4-group crosses the border: byte loads / fill value
+          const unsigned char* row = img + (size_t)sy * a.W;
+          const unsigned char fv = (unsigned char)0;
+          q[m].x = sx[0] >= 0 ? row[sx[0]] : fv; q[m].y = sx[1] >= 0 ? row[sx[1]] : fv;
+          q[m].z = sx[2] >= 0 ? row[sx[2]] : fv; q[m].w = sx[3] >= 0 ? row[sx[3]] : fv;
+          if (sx[0] < 0 || sx[1] < 0 || sx[2] < 0 || sx[3] < 0) fillmask |= 0x10000u << m;  // per-pixel fill needed
+        }
+      }
+    };
+    auto store_batch = [&](int ib, const uchar4 (&q)[RIF], unsigned fillmask) {
+#pragma unroll
+      for (int m = 0; m < RIF; ++m) {
+        const int i = ib + m * rstep;
+        if (i < i_end) {
+          float v[4] = {(float)q[m].x, (float)q[m].y, (float)q[m].z, (float)q[m].w};
+          if (fillmask & (1u << m)) v[0] = v[1] = v[2] = v[3] = a.bval[0];
+          if (fillmask & (0x10000u << m)) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (sx[e] < 0) v[e] = a.bval[0];
+          }
+          if (a.has_affine) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __fadd_rn(__fmul_rn(v[e], a.scale[0]), a.bias[0]);
+          }
+          __stcs(reinterpret_cast<float4*>(o_col + (size_t)i * a.Tw), make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+    };
+    int i0 = i_begin + rsub;
+    if (PIPE) {
+      uchar4 qa[RIF], qb[RIF];
+      unsigned fa, fb;
+      load_batch(i0, qa, fa);
+      while (i0 < i_end) {
+        load_batch(i0 + step, qb, fb);
+        store_batch(i0, qa, fa);
+        i0 += step;
+        if (i0 >= i_end) break;
+        load_batch(i0 + step, qa, fa);
+        store_batch(i0, qb, fb);
+        i0 += step;
+      }
+    } else {
+      for (; i0 < i_end; i0 += step) {
+        uchar4 q[RIF];
+        unsigned f;
+        load_batch(i0, q, f);
+        store_batch(i0, q, f);
+      }
+    }
+  }
+}
+
+static int sv_slice_variant() {
+  const char* v = getenv("TB200_SV_SLICE");
+  return v ? atoi(v) : 1;
+}
+
 cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStream_t s) {
   if (a.views.count != 1 || (a.Tw % 4) || !al16(a.out) || a.n > 65535 || a.n <= 0) return cudaErrorNotSupported;
   // enough CTAs for >= 8 waves of the ~5-8 resident CTAs per SM (a tail wave then costs <= ~1/8 of a wave), but bands no
@@ -339,6 +383,17 @@ cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStre
   const int want = (sm_count() * 8 * 8 + a.n - 1) / a.n;
   const int bands = std::max(1, std::min(std::max(1, a.Th / min_rows), want));
   dim3 grid((unsigned)bands, (unsigned)a.n);
+  if (img_dtype == TB_U8 && a.C == 1) {
+    switch (sv_slice_variant()) {  // A/B switch (TB200_SV_SLICE); default = the fastest measured on cfg 5
+      case 0: slice_u8c1_kernel<4, false, 6><<<grid, kSV, 0, s>>>(a); break;
+      case 2: slice_u8c1_kernel<8, false, 6><<<grid, kSV, 0, s>>>(a); break;
+      case 3: slice_u8c1_kernel<16, false, 3><<<grid, kSV, 0, s>>>(a); break;
+      case 4: slice_u8c1_kernel<4, true, 6><<<grid, kSV, 0, s>>>(a); break;
+      case 5: slice_u8c1_kernel<8, true, 4><<<grid, kSV, 0, s>>>(a); break;
+      default: slice_u8c1_kernel<8, false, 4><<<grid, kSV, 0, s>>>(a); break;
+    }
+    return cudaGetLastError();
+  }
   switch (img_dtype) {
     case TB_U8: slice_single_view_kernel<unsigned char><<<grid, kSV, 0, s>>>(a); break;
     case TB_U16: slice_single_view_kernel<unsigned short><<<grid, kSV, 0, s>>>(a); break;
