@@ -360,12 +360,14 @@ struct RegionArgs {
 // binary / multilabel: rows are (b,c) pairs of `inner` contiguous elements
 template <int VW>
 __global__ void __launch_bounds__(kLT) region_stats_elem_kernel(RegionArgs a) {
-  const long long row = blockIdx.y;  // b*C + c
+  // 1-D grid: CTA = (row, chunk); rows = B*C may exceed the 65535 limit of gridDim.y
+  const long long row = blockIdx.x / a.chunks;  // b*C + c
+  const int chunk = (int)(blockIdx.x - row * a.chunks);
   const long long innerv = a.inner / VW;
   const float* xr = a.x + row * a.inner;
   const float* tr = static_cast<const float*>(a.t) + row * a.inner;
   double acc[3] = {0.0, 0.0, 0.0};
-  for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < innerv; v += (long long)gridDim.x * kLT) {
+  for (long long v = (long long)chunk * kLT + threadIdx.x; v < innerv; v += (long long)a.chunks * kLT) {
     float xs[VW], ts[VW];
     ld_vec<VW>(xr, v, xs);
     ld_vec<VW>(tr, v, ts);
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(kLT) region_stats_elem_kernel(RegionArgs a) {
   }
   block_reduce<3>(acc);
   if (threadIdx.x == 0) {
-    double* o = a.partials + ((size_t)row * gridDim.x + blockIdx.x) * 3;
+    double* o = a.partials + ((size_t)row * a.chunks + chunk) * 3;
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
   }
 }
@@ -575,6 +577,11 @@ __device__ __forceinline__ void region_class_terms(const tb_dice_params& p, cons
   beta = (float)(m * dl * ds_0);
 }
 
+}  // namespace tb
+#include "pixel_vec4.cuh"
+namespace tb {
+
+// VW: 1 / 4 = elementwise scalar / vector; 8 = multiclass with 4 pixels per thread (pixel_vec4.cuh), C <= 8
 template <int VW>
 __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
   extern __shared__ float sh_coef[];  // [C][2] alpha, beta (already divided by the number of averaged classes)
@@ -599,17 +606,22 @@ __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.loss_out) *a.loss_out = (float)sh_loss;
   if (!a.grad) return;
 
+  if (VW == 8) {
+    region_grad_mc_vec4<8>(a, sh_coef);
+    return;
+  }
   if (a.p.mode != 1) {
     // binary / multilabel: elementwise
-    const long long totalv = a.B * a.C * a.inner / VW, innerv = a.inner / VW;
+    constexpr int EV = VW == 8 ? 1 : VW;
+    const long long totalv = a.B * a.C * a.inner / EV, innerv = a.inner / EV;
     for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < totalv; v += (long long)gridDim.x * kLT) {
       const int c = (int)((v / innerv) % a.C);
       const float al = sh_coef[2 * c], be = sh_coef[2 * c + 1];
-      float xs[VW], ts[VW], g[VW];
-      ld_vec<VW>(a.x, v, xs);
-      ld_vec<VW>(static_cast<const float*>(a.t), v, ts);
+      float xs[EV], ts[EV], g[EV];
+      ld_vec<EV>(a.x, v, xs);
+      ld_vec<EV>(static_cast<const float*>(a.t), v, ts);
 #pragma unroll
-      for (int e = 0; e < VW; ++e) {
+      for (int e = 0; e < EV; ++e) {
         const float t = ts[e];
         const bool ign = a.p.has_ignore && t == a.p.ignore_index;
         float dp = 1.f;
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
         }
         g[e] = ign ? 0.f : (al * t + be) * dp;
       }
-      st_vec<VW>(a.grad, v, g);
+      st_vec<EV>(a.grad, v, g);
     }
   } else {
     const long long npix = a.B * a.inner;
@@ -739,7 +751,8 @@ __device__ __forceinline__ void joint_elem(const JointArgs& a, float x, float t,
 
 template <int VW, bool FAST>
 __global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
-  const long long row = blockIdx.y;  // b*C + c
+  const long long row = blockIdx.x / a.chunks;  // b*C + c (1-D grid: rows may exceed the gridDim.y limit)
+  const int chunk = (int)(blockIdx.x - row * a.chunks);
   const int c = (int)(row % a.C);
   const long long innerv = a.inner / VW;
   const float* xr = a.x + row * a.inner;
@@ -747,7 +760,7 @@ __global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   float part[4] = {0.f, 0.f, 0.f, 0.f};  // float partials over a few vectors, flushed into the doubles every 4th trip
   int trips = 0;
-  for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < innerv; v += (long long)gridDim.x * kLT) {
+  for (long long v = (long long)chunk * kLT + threadIdx.x; v < innerv; v += (long long)a.chunks * kLT) {
     float xs[VW], ts[VW];
     ld_vec<VW>(xr, v, xs);
     ld_vec<VW>(tr, v, ts);
@@ -778,7 +791,7 @@ __global__ void __launch_bounds__(kLT) joint_stats_kernel(JointArgs a) {
   for (int q = 0; q < 4; ++q) acc[q] += (double)part[q];
   block_reduce<4>(acc);
   if (threadIdx.x == 0) {
-    double* o = a.partials + ((size_t)row * gridDim.x + blockIdx.x) * 4;
+    double* o = a.partials + ((size_t)row * a.chunks + chunk) * 4;
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
   }
 }
@@ -1080,7 +1093,17 @@ int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C,
   double* sums = partials + 2 * (size_t)grid;
   a.partials = partials; a.sums = nullptr;
   float* scalar_out = (elem_out || batchwise) ? nullptr : loss_out;
-  if (!normalized) {
+  const bool quads = !normalized && !has_reduced_threshold && C <= 8 && (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(t) & 15) == 0 && (!grad || (reinterpret_cast<uintptr_t>(grad) & 15) == 0) &&
+                     (!elem_buf || (reinterpret_cast<uintptr_t>(elem_buf) & 15) == 0);
+  if (quads) {
+    const int gq = loss_grid(B * inner / 4);
+    a.partials = partials;
+    double* sums_q = partials + 2 * (size_t)gq;
+    if (C <= 4) softmax_focal_vec4_kernel<4><<<gq, kLT, 0, s>>>(a);
+    else softmax_focal_vec4_kernel<8><<<gq, kLT, 0, s>>>(a);
+    focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, gq, sums_q, scalar_out, reduction, 0, eps, npos);
+  } else if (!normalized) {
     launch_pixel_focal<0>(a, grid, s);
     focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, scalar_out, reduction, 0, eps, npos);
   } else {
@@ -1109,8 +1132,13 @@ int tb_dice_stats(const float* x, const void* t, int t_kind, int64_t B, int C, i
   if (p->mode == 1) {
     TB_REQUIRE(t_kind == TB_T_LABELS_I64, TB_ERR_ARG, "tb_dice_stats: multiclass needs int64 labels");
     TB_REQUIRE(C <= 1024, TB_ERR_UNSUPPORTED, "tb_dice_stats: multiclass supports C <= 1024");
-    const int grid = loss_grid(B * inner);
-    if (C <= 4)
+    const bool quads = (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 && C <= 8;
+    const int grid = loss_grid(quads ? B * inner / 4 : B * inner);
+    if (quads && C <= 4)
+      region_stats_mc_vec4_kernel<4><<<grid, kLT, 0, s>>>(a);
+    else if (quads)
+      region_stats_mc_vec4_kernel<8><<<grid, kLT, 0, s>>>(a);
+    else if (C <= 4)
       region_stats_mc_small_kernel<4><<<grid, kLT, 0, s>>>(a);
     else if (C <= 8)
       region_stats_mc_small_kernel<8><<<grid, kLT, 0, s>>>(a);
@@ -1119,12 +1147,12 @@ int tb_dice_stats(const float* x, const void* t, int t_kind, int64_t B, int C, i
     region_stats_mc_finalize<<<C, kLT, 0, s>>>(a.partials, grid, C, stats_out);
   } else {
     TB_REQUIRE(t_kind == TB_T_DENSE_F32, TB_ERR_ARG, "tb_dice_stats: binary/multilabel need a dense f32 target");
-    TB_REQUIRE(B * C <= 65535, TB_ERR_UNSUPPORTED, "tb_dice_stats: B*C must be <= 65535");
     const bool vec4 = (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0;
     const long long innerv = inner / (vec4 ? 4 : 1);
     const int chunks = (int)std::max<long long>(1, std::min<long long>(64, (innerv + kLT * 4 - 1) / (kLT * 4)));
     a.chunks = chunks;
-    dim3 grid(chunks, (unsigned)(B * C));
+    TB_REQUIRE((long long)B * C * chunks < (1ll << 31), TB_ERR_UNSUPPORTED, "tb_dice_stats: too many (batch, class) rows");
+    const unsigned grid = (unsigned)((long long)B * C * chunks);
     if (vec4)
       region_stats_elem_kernel<4><<<grid, kLT, 0, s>>>(a);
     else
@@ -1147,17 +1175,21 @@ int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t B, int 
   a.x = x; a.t = t; a.t_kind = t_kind; a.B = B; a.inner = inner; a.C = C; a.p = *p;
   a.stats = stats; a.classes = classes; a.n_classes = n_classes; a.grad = grad; a.loss_out = loss_out;
   int grid = 1;
-  bool vec4 = false;
+  bool vec4 = false, mc_quads = false;
   if (grad) {
     if (p->mode == 1) {
-      grid = loss_grid(B * inner);
+      mc_quads = p->from_logits && C <= 8 && (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(t) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
+      grid = loss_grid(mc_quads ? B * inner / 4 : B * inner);
     } else {
       vec4 = (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
       grid = loss_grid(B * C * inner / (vec4 ? 4 : 1));
     }
   }
-  if (vec4)
+  if (mc_quads)
+    region_grad_kernel<8><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
+  else if (vec4)
     region_grad_kernel<4><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
   else
     region_grad_kernel<1><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
@@ -1175,7 +1207,7 @@ int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int6
              TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: focal term must be sigmoid, not normalised, mean or sum reduced");
   TB_REQUIRE((dp->mode == 0 || dp->mode == 2) && dp->from_logits, TB_ERR_UNSUPPORTED,
              "tb_focal_dice_fwd_bwd: region term must be binary / multilabel on logits");
-  TB_REQUIRE(B * C <= 65535 && C <= 4096, TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: B*C must be <= 65535, C <= 4096");
+  TB_REQUIRE(C <= 4096, TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: C <= 4096");
   TB_REQUIRE(!classes || n_classes > 0, TB_ERR_ARG, "tb_focal_dice_fwd_bwd: empty class list");
   TB_REQUIRE(ws_bytes >= tb_loss_workspace_bytes(B, C, inner), TB_ERR_WORKSPACE, "tb_focal_dice_fwd_bwd: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1192,7 +1224,8 @@ int tb_focal_dice_fwd_bwd(const float* x, const float* t, int64_t B, int C, int6
   a.chunks = chunks;
   a.partials = static_cast<double*>(ws);
   a.stats = a.partials + (size_t)B * C * chunks * 4;
-  dim3 grid1(chunks, (unsigned)(B * C));
+  TB_REQUIRE((long long)B * C * chunks < (1ll << 31), TB_ERR_UNSUPPORTED, "tb_focal_dice_fwd_bwd: too many (batch, class) rows");
+  const unsigned grid1 = (unsigned)((long long)B * C * chunks);
   // the common configuration (BinaryFocalLoss() + DiceLoss / JaccardLoss without ignore_index) takes the branch-free kernels
   const bool fast = vec4 && fp->gamma == 2.f && !fp->has_alpha && !class_w && !fp->has_ignore && !fp->has_reduced_threshold &&
                     !dp->has_ignore;

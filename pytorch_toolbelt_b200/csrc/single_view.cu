@@ -43,9 +43,9 @@ __device__ __forceinline__ void ldcs4(const float* p, float v[4]) {
 // inner loop is then: address = base + k*plane + (y - ty)*Tw + (x - tx), no per-thread coverage test, no index arithmetic.
 constexpr int kSvMaxTiles = 16;  // covering tiles per unit the list holds (4x4); larger covering sets -> general kernels
 
-template <int UW, int WK, bool PLAIN>
-__global__ void __launch_bounds__(kSV, 3) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
-                                                                  int nux, int ux0) {
+template <int UW, int WK, bool PLAIN, int MINB = 3>
+__global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
+                                                                     int nux, int ux0) {
   constexpr int LPR = UW / 4;        // lanes per unit row
   constexpr int RPP = kSV / LPR;     // rows per pass
   constexpr int PASSES = 32 / RPP;
@@ -215,6 +215,16 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   const int passes = wide ? 4 : 1;
   const bool split = passes > 1 && units < (long long)sm_count() * 3 * 8;
   const dim3 grid((unsigned)units, split ? passes : 1);
+  // A/B switch on the register budget of the common instances (TB200_SV_MERGE = resident CTAs per SM: 2..5; default 3)
+  const char* mv = getenv("TB200_SV_MERGE");
+  const int minb = mv ? atoi(mv) : 3;
+  if (wide && plain && wk <= 1 && minb != 3) {
+#define TB_SV_MB(WK_, MB) merge_single_view_kernel<128, WK_, true, MB><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
+    if (wk == 0) { if (minb == 2) TB_SV_MB(0, 2); else if (minb == 4) TB_SV_MB(0, 4); else TB_SV_MB(0, 5); }
+    else { if (minb == 2) TB_SV_MB(1, 2); else if (minb == 4) TB_SV_MB(1, 4); else TB_SV_MB(1, 5); }
+#undef TB_SV_MB
+    return cudaGetLastError();
+  }
 #define TB_SV(UW, WK_, PLAIN_) merge_single_view_kernel<UW, WK_, PLAIN_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
 #define TB_SV_WK(UW, PLAIN_) do { if (wk == 0) TB_SV(UW, 0, PLAIN_); else if (wk == 1) TB_SV(UW, 1, PLAIN_); else TB_SV(UW, 2, PLAIN_); } while (0)
   if (wide) {
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(kSV, MINB) slice_u8c1_kernel(SliceArgs a) {
 
 static int sv_slice_variant() {
   const char* v = getenv("TB200_SV_SLICE");
-  return v ? atoi(v) : 1;
+  return v ? atoi(v) : 0;  // measured on cfg 5 (profiles/r2_single_view_variants.md): occupancy beats rows in flight
 }
 
 cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStream_t s) {
@@ -385,12 +395,15 @@ cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStre
   dim3 grid((unsigned)bands, (unsigned)a.n);
   if (img_dtype == TB_U8 && a.C == 1) {
     switch (sv_slice_variant()) {  // A/B switch (TB200_SV_SLICE); default = the fastest measured on cfg 5
-      case 0: slice_u8c1_kernel<4, false, 6><<<grid, kSV, 0, s>>>(a); break;
+      case 1: slice_u8c1_kernel<8, false, 4><<<grid, kSV, 0, s>>>(a); break;
+      case 6: slice_u8c1_kernel<2, false, 8><<<grid, kSV, 0, s>>>(a); break;
+      case 7: slice_u8c1_kernel<4, false, 8><<<grid, kSV, 0, s>>>(a); break;
+      case 8: slice_u8c1_kernel<1, false, 8><<<grid, kSV, 0, s>>>(a); break;
       case 2: slice_u8c1_kernel<8, false, 6><<<grid, kSV, 0, s>>>(a); break;
       case 3: slice_u8c1_kernel<16, false, 3><<<grid, kSV, 0, s>>>(a); break;
       case 4: slice_u8c1_kernel<4, true, 6><<<grid, kSV, 0, s>>>(a); break;
       case 5: slice_u8c1_kernel<8, true, 4><<<grid, kSV, 0, s>>>(a); break;
-      default: slice_u8c1_kernel<8, false, 4><<<grid, kSV, 0, s>>>(a); break;
+      default: slice_u8c1_kernel<4, false, 6><<<grid, kSV, 0, s>>>(a); break;
     }
     return cudaGetLastError();
   }

@@ -236,3 +236,13 @@ def test_reference_known_answer_tests():
     xg = x.clone().requires_grad_(True)
     L.BinaryFocalLoss()(xg, y).backward()
     assert xg.grad is not None and xg.grad.device.type == "cpu"
+
+
+def test_more_than_65535_batch_class_rows():
+    """(batch, class) rows used to ride on gridDim.y (<= 65535); the stats kernels now fold them into gridDim.x."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(70000, 1, 4, 4, generator=g) * 2
+    t = (torch.rand(70000, 1, 4, 4, generator=g) < 0.4).float()
+    _cmp_oracle(lambda z: L.DiceLoss("binary")(z, t.cuda()), lambda z: LO.dice_loss(z, t, "binary"), x)
+    _cmp_oracle(lambda z: L.BinaryFocalDiceLoss(L.BinaryFocalLoss(), L.DiceLoss("binary"))(z, t.cuda()),
+                lambda z: LO.focal_sigmoid(z, t, alpha=None) + LO.dice_loss(z, t, "binary"), x)
