@@ -338,6 +338,93 @@ __global__ void __launch_bounds__(kLT) pixel_focal_kernel(PixelFocalArgs a) {
   }
 }
 
+// softmax_focal_loss_with_logits for ANY class count (C > 64: ADE20K-sized label sets): nothing is held per channel, the
+// logits of a pixel are re-read from L1/L2 in four sweeps (max, denominator, loss + the two softmax-backward sums, gradient).
+template <int PASS>
+__global__ void __launch_bounds__(kLT) pixel_focal_anyc_kernel(PixelFocalArgs a) {
+  const long long npix = a.B * a.inner;
+  const tb_focal_params& p = a.f.p;
+  double acc[2] = {0.0, 0.0};
+  float invN = 1.f, coefF = 0.f;
+  if (PASS == 2) {
+    const double N = fmax(a.sums[1], (double)p.eps);
+    invN = (float)(1.0 / N);
+    coefF = (a.sums[1] > (double)p.eps) ? (float)(a.sums[0] / (N * N)) : 0.f;
+  }
+  for (long long pix = (long long)blockIdx.x * kLT + threadIdx.x; pix < npix; pix += (long long)gridDim.x * kLT) {
+    const long long b = pix / a.inner, pos = pix - b * a.inner;
+    const float* xp = a.x + b * a.C * a.inner + pos;
+    const long long lab = __ldg(static_cast<const long long*>(a.t) + pix);
+    const bool valid = lab != a.ignore_label;
+    const int label = valid ? (int)lab : 0;
+    float mx = -INFINITY;
+    for (int c = 0; c < a.C; ++c) mx = fmaxf(mx, __ldg(xp + (long long)c * a.inner));
+    float den = 0.f;
+    for (int c = 0; c < a.C; ++c) den += __expf(__ldg(xp + (long long)c * a.inner) - mx);
+    const float inv_den = 1.f / den;
+    auto terms = [&](int c, float& prob, float& G, float& direct, float& Fd, float& focal, float& bce_w) {
+      const float x = __ldg(xp + (long long)c * a.inner);
+      prob = __expf(x - mx) * inv_den;
+      const float oh = (c == label) ? 1.f : 0.f;
+      const float pt = (1.f - oh) * prob + oh * (1.f - prob);
+      const float dpt_dp = 1.f - 2.f * oh;
+      float dfocal_dp;
+      if (!p.has_reduced_threshold) {
+        focal = powg(pt, p.gamma);
+        dfocal_dp = dpowg(pt, p.gamma) * dpt_dp;
+      } else if (pt < p.reduced_threshold) {
+        focal = 1.f;
+        dfocal_dp = 0.f;
+      } else {
+        const float inv = 1.f / p.reduced_threshold;
+        focal = powg(pt * inv, p.gamma);
+        dfocal_dp = dpowg(pt * inv, p.gamma) * inv * dpt_dp;
+      }
+      const float bce = bce_logits(x, oh);
+      const float w = a.f.cw ? __ldg(a.f.cw + c) : 1.f;
+      bce_w = focal * bce * w;
+      G = valid ? w * bce * dfocal_dp : 0.f;
+      direct = valid ? w * focal * (sigmoidf_(x) - oh) : 0.f;
+      Fd = dfocal_dp;
+    };
+    float Lpix = 0.f, Fpix = 0.f, S_G = 0.f, S_F = 0.f;
+    for (int c = 0; c < a.C; ++c) {
+      float prob, G, direct, Fd, focal, bw;
+      terms(c, prob, G, direct, Fd, focal, bw);
+      Lpix += bw;
+      Fpix += focal;
+      S_G += G * prob;
+      S_F += Fd * prob;
+    }
+    if (!valid) Lpix = 0.f;
+    if (PASS != 2) {
+      acc[0] += (double)Lpix;
+      acc[1] += (double)Fpix;
+    }
+    if (PASS != 1) {
+      if (a.loss_elem) a.loss_elem[pix] = (PASS == 2) ? Lpix * invN : Lpix;
+      if (a.grad) {
+        float* gp = a.grad + b * a.C * a.inner + pos;
+        for (int c = 0; c < a.C; ++c) {
+          float prob, G, direct, Fd, focal, bw;
+          terms(c, prob, G, direct, Fd, focal, bw);
+          const float dL = prob * (G - S_G) + direct;
+          float g = dL;
+          if (PASS == 2) g = dL * invN - coefF * prob * (Fd - S_F);
+          gp[(long long)c * a.inner] = g * a.gscale;
+        }
+      }
+    }
+  }
+  if (PASS != 2) {
+    block_reduce<2>(acc);
+    if (threadIdx.x == 0) {
+      a.partials[2 * blockIdx.x] = acc[0];
+      a.partials[2 * blockIdx.x + 1] = acc[1];
+    }
+  }
+}
+
 // =================================================================================================
 // dice / jaccard
 // =================================================================================================
@@ -968,6 +1055,10 @@ size_t tb_loss_workspace_bytes(int64_t B, int C, int64_t inner) {
 
 template <int PASS>
 static void launch_pixel_focal(const PixelFocalArgs& a, int grid, cudaStream_t s) {
+  if (a.C > kMaxC && a.mode == 0) {
+    pixel_focal_anyc_kernel<PASS><<<grid, kLT, 0, s>>>(a);
+    return;
+  }
   if (a.C <= 4) pixel_focal_kernel<PASS, 4><<<grid, kLT, 0, s>>>(a);
   else if (a.C <= 8) pixel_focal_kernel<PASS, 8><<<grid, kLT, 0, s>>>(a);
   else if (a.C <= 16) pixel_focal_kernel<PASS, 16><<<grid, kLT, 0, s>>>(a);
@@ -1073,7 +1164,6 @@ int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C,
                              size_t ws_bytes, void* stream) {
   TB_REQUIRE(x && t && loss_out && ws, TB_ERR_ARG, "tb_softmax_focal_fwd_bwd: null pointer");
   TB_REQUIRE(B > 0 && C > 0 && inner > 0, TB_ERR_ARG, "tb_softmax_focal_fwd_bwd: bad shape");
-  TB_REQUIRE(C <= kMaxC, TB_ERR_UNSUPPORTED, "tb_softmax_focal_fwd_bwd: supports C <= %d", kMaxC);
   TB_REQUIRE(reduction_ok(reduction), TB_ERR_ARG, "tb_softmax_focal_fwd_bwd: bad reduction %d", reduction);
   TB_REQUIRE(ws_bytes >= tb_loss_workspace_bytes(B, C, inner), TB_ERR_WORKSPACE, "tb_softmax_focal_fwd_bwd: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;

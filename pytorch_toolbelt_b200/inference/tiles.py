@@ -306,7 +306,10 @@ class TileMerger:
 
     ``device="cpu"`` (the reference default) is honoured as "hand results back on the CPU": accumulation still
     runs in the CUDA engine on the current CUDA device (there is no CPU implementation), ``image`` / ``norm_mask``
-    / ``merge()`` return CPU copies.
+    / ``merge()`` return CPU copies. Those copies are cached per accumulator state: reading ``merger.image`` twice
+    downloads the canvas once (it is 419 MB at BASELINE config 2), and again only after the next ``integrate_batch``
+    / ``merge_`` / assignment. Treat the returned CPU tensors as read-only snapshots (in-place edits do not reach the GPU
+    state -- assign to ``merger.image`` for that).
     """
 
     def __init__(self, image_shape, channels, weight, device="cpu", dtype=torch.float32):
@@ -332,30 +335,46 @@ class TileMerger:
         self._weight = torch.from_numpy(np.expand_dims(weight, axis=0)).to(device=self._dev, dtype=dtype).contiguous()
         self._image = torch.zeros((channels, self.image_height, self.image_width), device=self._dev, dtype=dtype)
         self._norm_mask = torch.zeros((1, self.image_height, self.image_width), device=self._dev, dtype=dtype)
+        self._version = 0      # bumped whenever the accumulator changes
+        self._host_cache = {}  # name -> (version, CPU copy)
 
-    # plain tensors, like the reference's attributes (tiles.py:306-308); CPU-requesting mergers get copies
-    def _present(self, t: torch.Tensor) -> torch.Tensor:
-        return t if self._out_device.type == "cuda" else t.to(self._out_device)
+    # plain tensors, like the reference's attributes (tiles.py:306-308); CPU-requesting mergers get (cached) copies
+    def _present(self, t: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:
+        if self._out_device.type == "cuda":
+            return t
+        if name is None:
+            return t.to(self._out_device)
+        hit = self._host_cache.get(name)
+        if hit is None or hit[0] != self._version:
+            hit = (self._version, t.to(self._out_device))
+            self._host_cache[name] = hit
+        return hit[1]
+
+    def _touch(self):
+        self._version += 1
+        self._host_cache.clear()
 
     @property
     def image(self) -> torch.Tensor:
-        return self._present(self._image)
+        return self._present(self._image, "image")
 
     @image.setter
     def image(self, value: torch.Tensor):
         self._image = value.to(device=self._dev, dtype=self._dtype).contiguous()
+        self._touch()
 
     @property
     def norm_mask(self) -> torch.Tensor:
-        return self._present(self._norm_mask)
+        return self._present(self._norm_mask, "norm_mask")
 
     @norm_mask.setter
     def norm_mask(self, value: torch.Tensor):
         self._norm_mask = value.to(device=self._dev, dtype=self._dtype).contiguous()
+        self._touch()
 
     @property
     def weight(self) -> torch.Tensor:
-        return self._present(self._weight)
+        return self._present(self._weight, "weight")
 
     @property
     def device(self) -> torch.device:
@@ -412,6 +431,7 @@ class TileMerger:
                 N.stream_ptr(self._dev),
             )
         N.check(rc, "tb_deaugment_merge")
+        self._touch()
         del keep
 
     def _normalized(self, eps: float = -1.0, top: int = 0, left: int = 0, height: Optional[int] = None,
@@ -434,7 +454,8 @@ class TileMerger:
 
     def merge_(self) -> torch.Tensor:
         self._normalized(out=self._image)
-        return self._present(self._image)
+        self._touch()
+        return self._present(self._image, "image")
 
 
 class CudaTileMerger(TileMerger):

@@ -246,3 +246,18 @@ def test_more_than_65535_batch_class_rows():
     _cmp_oracle(lambda z: L.DiceLoss("binary")(z, t.cuda()), lambda z: LO.dice_loss(z, t, "binary"), x)
     _cmp_oracle(lambda z: L.BinaryFocalDiceLoss(L.BinaryFocalLoss(), L.DiceLoss("binary"))(z, t.cuda()),
                 lambda z: LO.focal_sigmoid(z, t, alpha=None) + LO.dice_loss(z, t, "binary"), x)
+
+
+def test_cross_entropy_focal_with_150_classes():
+    """the pixel-wise focal kernels held <= 64 channels in registers; larger label sets now take the any-C kernel."""
+    g = torch.Generator().manual_seed(12)
+    C = 150
+    x = torch.randn(2, C, 24, 20, generator=g) * 2
+    lab = torch.randint(0, C, (2, 24, 20), generator=g)
+    lab[torch.rand(2, 24, 20, generator=g) < 0.05] = -100
+    cw = torch.rand(C, generator=g) + 0.5
+    _cmp_oracle(lambda z: L.CrossEntropyFocalLoss()(z, lab.cuda()), lambda z: LO.focal_softmax(z, lab), x)
+    _cmp_oracle(lambda z: L.CrossEntropyFocalLoss(gamma=1.5, normalized=True, class_weights=cw)(z, lab.cuda()),
+                lambda z: LO.focal_softmax(z, lab, gamma=1.5, normalized=True, class_weights=cw), x)
+    _cmp_oracle(lambda z: L.CrossEntropyFocalLoss(reduced_threshold=0.4, reduction="sum")(z, lab.cuda()),
+                lambda z: LO.focal_softmax(z, lab, reduced_threshold=0.4, reduction="sum"), x)
