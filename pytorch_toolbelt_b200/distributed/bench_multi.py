@@ -106,6 +106,28 @@ def run_multi_gpu(args, CFG, cfg_name, METRIC, UNIT, WORKLOAD):
     clk = clocks.summary()
     merger.check()
 
+    # where a step goes, per rank (CUDA events between the launches of 5 untimed steps; max and min over ranks)
+    def phase_probe():
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        marks[0].record()
+        slicer.run()
+        marks[1].record()
+        merger.run(marks=marks[2:3])
+        marks[3].record()
+        return marks
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    probes = [phase_probe() for _ in range(5)]
+    torch.cuda.synchronize()
+    ph = torch.zeros(3, device=dev)
+    for m in probes[1:]:
+        ph += torch.tensor([m[0].elapsed_time(m[1]), m[1].elapsed_time(m[2]), m[2].elapsed_time(m[3])], device=dev)
+    ph /= len(probes) - 1
+    ph_max, ph_min = ph.clone(), ph.clone()
+    dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
+
     # e2e through the public API with host buffers: every rank uploads ITS image slab, runs its tile range, downloads the
     # rows its pixels lie in (the seam rows are downloaded by both neighbours; each holds its own pixels of them)
     oy0, oy1 = iy0, iy1
@@ -153,10 +175,14 @@ def run_multi_gpu(args, CFG, cfg_name, METRIC, UNIT, WORKLOAD):
             },
             "with_model": {"value": mp / (ms_with_model * 1e-3), "unit": UNIT, "ms_per_step": ms_with_model},
             "phases_ms_max_over_ranks": {"slice": ms_slice, "merge_with_exchange": ms_merge},
+            "phases_ms_inside_a_step": {"what": "CUDA events between the launches of one step, mean of 4 steps: [max over ranks, min over ranks]",
+                                        "slice": [float(ph_max[0]), float(ph_min[0])],
+                                        "ack_wait+spill_merge+signal": [float(ph_max[1]), float(ph_min[1])],
+                                        "ready_wait+final_and_seeded_merge+ack": [float(ph_max[2]), float(ph_min[2])]},
             "e2e": {"value": mp / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(slab[0].item()), "d2h_bytes_per_step": int(slab[1].item()),
                     "api": "per rank: pinned host image SLAB -> slice / model / RaggedMerger on its tile range -> pinned host rows"},
-            "gpu_launches": (1 + 3 + 4) * args.steps,
+            "gpu_launches": (1 + 2 + 4) * args.steps,
             "roofline_step": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_step * 1e-3) / 1e9, "peak": peak * world,
                               "frac": b_alg / (ms_step * 1e-3) / 1e9 / (peak * world), "unit": "GB/s",
                               "note": "whole-job algorithmic bytes / max-over-ranks step time / (N x measured single-GPU peak)"},

@@ -206,17 +206,20 @@ class RaggedMerger:
             return engine.merge_plan(preds, out=out, rows=rows, output=output, threshold=threshold,
                                      first_tile=plan.t0, peer=peer(mask, parity))
 
-        self.spill = self.final = self.seeded = (None, None)
+        # Two merge launches per step: (A) the unseeded SPILL blocks first, so that the next rank's seeds are on their way as
+        # early as possible; (B) everything else -- FINAL and, after the wait for the previous rank's flag, the SEEDED blocks --
+        # in ONE launch: by the time A has run here, the previous rank's A (same size, started at the same time) has run too,
+        # so the wait in front of B costs nothing and a third launch (its ramp-up and tail) is saved.
+        self.spill = self.rest = (None, None)
         if plan.next is not None:
             self.spill = tuple(launch(PH_SPILL, (plan.spill_y0, plan.spill_y0 + win), p) for p in (0, 1))
-        self.final = tuple(launch(PH_FINAL, (y0, y1), p) for p in (0, 1))
-        if plan.prev is not None:
-            # (the last rank has nobody to spill to -- and no block of its range can need it)
-            seeded_mask = PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
-            self.seeded = tuple(launch(seeded_mask, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
+        rest_mask = PH_FINAL
+        if plan.prev is not None:  # (the last rank has nobody to spill to -- and no block of its range can need it)
+            rest_mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
+        self.rest = tuple(launch(rest_mask, (y0, y1), p) for p in (0, 1))
 
-    def run(self):
-        """One step (epoch): [wait ack] spill -> [signal] final -> wait ready -> seeded [-> signal] -> ack."""
+    def run(self, marks=None):
+        """One step (epoch): [wait ack] spill -> signal(ready) -> wait(ready) -> final + seeded [-> signal if chained] -> ack."""
         N, plan, mb = self.N, self.plan, self.mailbox
         lib = N.lib()
         self.epoch += 1
@@ -231,12 +234,12 @@ class RaggedMerger:
                     self.spill[p].run()
                 if not plan.chained:
                     N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
-            if self.final[p] is not None:
-                self.final[p].run()
+            if marks:  # (bench instrumentation: an event between the two halves of the step)
+                marks[0].record(torch.cuda.current_stream(dev))
             if plan.prev is not None:
                 N.check(lib.tb_peer_wait(mb.ready(), e, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ready)")
-                if self.seeded[p] is not None:
-                    self.seeded[p].run()
+            if self.rest[p] is not None:
+                self.rest[p].run()
             if plan.next is not None and plan.chained:
                 N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
             if plan.prev is not None:
