@@ -43,7 +43,7 @@ __device__ __forceinline__ void ldcs4(const float* p, float v[4]) {
 // inner loop is then: address = base + k*plane + (y - ty)*Tw + (x - tx), no per-thread coverage test, no index arithmetic.
 constexpr int kSvMaxTiles = 16;  // covering tiles per unit the list holds (4x4); larger covering sets -> general kernels
 
-template <int UW, int WK, bool PLAIN, int MINB = 3>
+template <int UW, int WK, bool PLAIN, int MINB = 4, int CH = 4>
 __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllArgs a, const __grid_constant__ BatchPtrs ptrs,
                                                                      int nux, int ux0) {
   constexpr int LPR = UW / 4;        // lanes per unit row
@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllAr
         den[0] = d4.x; den[1] = d4.y; den[2] = d4.z; den[3] = d4.w;
       }
 #pragma unroll 1
-      for (int u0 = 0; u0 < nt; u0 += 4) {  // (nt <= 4 almost always: one trip)
-        float pv[4][4], wv[4][4];
+      for (int u0 = 0; u0 < nt; u0 += CH) {  // CH tiles' loads in flight before any is consumed
+        float pv[CH][4], wv[CH][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < CH; ++u) {
           if (u0 + u < nt) {
             const int i = y - s_ty[u0 + u], j = x - s_tx[u0 + u];
             const int off = i * g.Tw + j;
@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllAr
               const float di = (float)i - a.w.hc;
               const float wi = __expf(-(di * di) * a.w.param);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) wv[u][e] = wi * wj[u][e];  // (WK == 1 is only launched with nt <= 4: u0 == 0)
+              for (int e = 0; e < 4; ++e) {  // (WK == 1 is only launched with nt <= 4; static index: u0 is 0 or CH)
+                float wjc = wj[u][e];
+                if (CH == 2 && u0 == 2) wjc = wj[(u + 2) & 3][e];
+                wv[u][e] = wi * wjc;
+              }
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) wv[u][e] = weight_at<float>(a.w, i, j + e);
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllAr
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < CH; ++u) {
           if (u0 + u < nt) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -215,13 +219,22 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   const int passes = wide ? 4 : 1;
   const bool split = passes > 1 && units < (long long)sm_count() * 3 * 8;
   const dim3 grid((unsigned)units, split ? passes : 1);
-  // A/B switch on the register budget of the common instances (TB200_SV_MERGE = resident CTAs per SM: 2..5; default 3)
+  // A/B switch on the register budget / loads in flight of the common instances: TB200_SV_MERGE = 10 * CH + resident CTAs
+  // per SM (default 44: 4 tiles in flight, 4 CTAs/SM = 64 registers; measured on cfg 5, profiles/r2_single_view_variants.md)
   const char* mv = getenv("TB200_SV_MERGE");
-  const int minb = mv ? atoi(mv) : 3;
-  if (wide && plain && wk <= 1 && minb != 3) {
-#define TB_SV_MB(WK_, MB) merge_single_view_kernel<128, WK_, true, MB><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
-    if (wk == 0) { if (minb == 2) TB_SV_MB(0, 2); else if (minb == 4) TB_SV_MB(0, 4); else TB_SV_MB(0, 5); }
-    else { if (minb == 2) TB_SV_MB(1, 2); else if (minb == 4) TB_SV_MB(1, 4); else TB_SV_MB(1, 5); }
+  const int var = mv ? atoi(mv) : 44;
+  if (wide && plain && wk <= 1 && var != 44) {
+#define TB_SV_MB(WK_, MB, CH_) merge_single_view_kernel<128, WK_, true, MB, CH_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
+#define TB_SV_VAR(WK_)                                                          \
+    switch (var) {                                                              \
+      case 43: TB_SV_MB(WK_, 3, 4); break;                                      \
+      case 24: TB_SV_MB(WK_, 4, 2); break;                                      \
+      case 25: TB_SV_MB(WK_, 5, 2); break;                                      \
+      case 26: TB_SV_MB(WK_, 6, 2); break;                                      \
+      default: TB_SV_MB(WK_, 4, 4); break;                                      \
+    }
+    if (wk == 0) { TB_SV_VAR(0) } else { TB_SV_VAR(1) }
+#undef TB_SV_VAR
 #undef TB_SV_MB
     return cudaGetLastError();
   }
@@ -381,7 +394,7 @@ __global__ void __launch_bounds__(kSV, MINB) slice_u8c1_kernel(SliceArgs a) {
 
 static int sv_slice_variant() {
   const char* v = getenv("TB200_SV_SLICE");
-  return v ? atoi(v) : 0;  // measured on cfg 5 (profiles/r2_single_view_variants.md): occupancy beats rows in flight
+  return v ? atoi(v) : 8;  // measured on cfg 5 (profiles/r2_single_view_variants.md): occupancy beats rows in flight
 }
 
 cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStream_t s) {
@@ -398,12 +411,12 @@ cudaError_t launch_slice_single_view(const SliceArgs& a, int img_dtype, cudaStre
       case 1: slice_u8c1_kernel<8, false, 4><<<grid, kSV, 0, s>>>(a); break;
       case 6: slice_u8c1_kernel<2, false, 8><<<grid, kSV, 0, s>>>(a); break;
       case 7: slice_u8c1_kernel<4, false, 8><<<grid, kSV, 0, s>>>(a); break;
-      case 8: slice_u8c1_kernel<1, false, 8><<<grid, kSV, 0, s>>>(a); break;
       case 2: slice_u8c1_kernel<8, false, 6><<<grid, kSV, 0, s>>>(a); break;
       case 3: slice_u8c1_kernel<16, false, 3><<<grid, kSV, 0, s>>>(a); break;
       case 4: slice_u8c1_kernel<4, true, 6><<<grid, kSV, 0, s>>>(a); break;
       case 5: slice_u8c1_kernel<8, true, 4><<<grid, kSV, 0, s>>>(a); break;
-      default: slice_u8c1_kernel<4, false, 6><<<grid, kSV, 0, s>>>(a); break;
+      case 0: slice_u8c1_kernel<4, false, 6><<<grid, kSV, 0, s>>>(a); break;
+      default: slice_u8c1_kernel<1, false, 8><<<grid, kSV, 0, s>>>(a); break;
     }
     return cudaGetLastError();
   }
