@@ -271,6 +271,20 @@ typedef struct tb_peer_plan {
   float* spill_num;      /* f32 [K, spill_rows, Wp] */
   float* spill_den;      /* f32 [spill_rows, Wp] */
   int spill_y0, spill_rows;
+  /* fused != 0 (TMA kernel, i.e. TTA groups with >= 2 views): ONE launch per step handles all classes in phase_mask in the order
+   * spill -> final -> seeded AND the flags: waits `*ack_flag >= epoch - 2` before its first spill store, publishes
+   * `*next_ready = epoch` after the last spill block of the grid (after the seeded pass when `chained`), waits
+   * `*ready_flag >= epoch` before its first seeded block, publishes `*prev_ack = epoch` after the last one. counters: 3 local
+   * uint64 words, zero-initialised once, never reset (they count arrivals; target = epoch * pipelines). epoch starts at 1. */
+  int fused, chained, has_next, has_prev;
+  uint64_t epoch;
+  uint64_t* counters;
+  const uint64_t* ready_flag;
+  const uint64_t* ack_flag;
+  uint64_t* next_ready;
+  uint64_t* prev_ack;
+  uint64_t* status;
+  int timeout_ms;
 } tb_peer_plan;
 
 typedef struct tb_merge_extra {

@@ -94,7 +94,10 @@ class PeerPlan(C.Structure):
 
     _fields_ = [("phase_mask", C.c_int), ("t0", C.c_int), ("t1", C.c_int), ("seed_num", C.c_void_p), ("seed_den", C.c_void_p),
                 ("seed_y0", C.c_int), ("seed_rows", C.c_int), ("spill_num", C.c_void_p), ("spill_den", C.c_void_p),
-                ("spill_y0", C.c_int), ("spill_rows", C.c_int)]
+                ("spill_y0", C.c_int), ("spill_rows", C.c_int),
+                ("fused", C.c_int), ("chained", C.c_int), ("has_next", C.c_int), ("has_prev", C.c_int), ("epoch", C.c_uint64),
+                ("counters", C.c_void_p), ("ready_flag", C.c_void_p), ("ack_flag", C.c_void_p), ("next_ready", C.c_void_p),
+                ("prev_ack", C.c_void_p), ("status", C.c_void_p), ("timeout_ms", C.c_int)]
 
 
 class MergeExtra(C.Structure):

@@ -200,6 +200,7 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptrs, cudaStream_t s) {
   const tb_grid& g = a.grid;
   if (a.views.count != 1) return cudaErrorNotSupported;
+  if (a.peer.fused) return cudaErrorInvalidValue;  // in-kernel flag handling needs the persistent (ordered) TMA kernel
   if ((g.Th % 32) || (g.Tw % 32) || (g.Sx % 32) || (g.Sy % 32) || (a.Wp % 4)) return cudaErrorNotSupported;
   if (!a.vec_ok && a.out_mode == TB_OUT_LOGITS && !a.raw) return cudaErrorNotSupported;
   if (a.w.kind == TB_W_TABLE && !al16(a.w.table)) return cudaErrorNotSupported;

@@ -1098,6 +1098,12 @@ __device__ __forceinline__ BlockWork block_work(const MergeAllArgs& a, int blk) 
   return w;
 }
 
+// fused ragged-strip launch: block classes handled by pass 0 / 1 / 2 (spill first: the neighbour waits for it; seeded last:
+// we wait for the neighbour)
+__device__ __forceinline__ int peer_pass_mask(int pass) {
+  return pass == 0 ? TB_PH_SPILL : (pass == 1 ? TB_PH_FINAL : (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL));
+}
+
 // Iterator over the resident covering tiles of a block, row-major (the reference's accumulation order).
 struct TileIter {
   int r, c;
@@ -1177,9 +1183,14 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
       int it = 0;
       const bool hint = (a.debug & 8) != 0;
       const uint64_t policy = hint ? l2_evict_first_policy() : 0ull;
+      const int npass = a.peer.fused ? 3 : 1;
+      for (int pass = 0; pass < npass; ++pass)
       for (int blk = blk0; blk < nblocks; blk += blk_step) {
         const BlockWork w = block_work(a, blk);
-        if (a.peer.phase_mask && !peer_block_class(a.peer, g.nx, w.ra, w.rb, w.ca, w.cb)) continue;  // (same test as the consumers)
+        if (a.peer.phase_mask) {  // (same test, same order as the consumers)
+          const int cls = peer_block_class(a.peer, g.nx, w.ra, w.rb, w.ca, w.cb);
+          if (!cls || (a.peer.fused && !(cls & peer_pass_mask(pass)))) continue;
+        }
         const int nt = block_tile_count(a, w);
         for (int k = 0; k < a.K; ++k) {
           int idx = 0, s = 0;
@@ -1227,12 +1238,25 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
 
   int it = 0;
   LabelState ls;
+  const int npass = a.peer.fused ? 3 : 1;
+  const unsigned long long arrivals = a.peer.epoch * (unsigned long long)(gridDim.x * NG);  // grid-wide target of the counters
+  const bool leader = (warp == 0 && lane == 0);  // one thread per pipeline talks to the flags
+  for (int pass = 0; pass < npass; ++pass) {
+  if (a.peer.fused) {
+    // ---- before the pass: the waits of the ragged-strip protocol, by one thread, then the pipeline's consumers meet ----
+    if (pass == 0 && a.peer.has_next && a.peer.epoch > 2 && leader)
+      peer_spin_until(a.peer.ack_flag, a.peer.epoch - 2, a.peer.timeout_ns, a.peer.status);   // double buffer free again?
+    if (pass == 2 && a.peer.has_prev && leader)
+      peer_spin_until(a.peer.ready_flag, a.peer.epoch, a.peer.timeout_ns, a.peer.status);     // seeds of this epoch complete?
+    if ((pass == 0 && a.peer.has_next && a.peer.epoch > 2) || (pass == 2 && a.peer.has_prev))
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + pipe), "r"(kTmaConsumerWarps * 32) : "memory");
+  }
   for (int blk = blk0; blk < nblocks; blk += blk_step) {
     const BlockWork w = block_work(a, blk);
     int cls = 0;
     if (a.peer.phase_mask) {
       cls = peer_block_class(a.peer, g.nx, w.ra, w.rb, w.ca, w.cb);
-      if (!cls) continue;
+      if (!cls || (a.peer.fused && !(cls & peer_pass_mask(pass)))) continue;
     }
     const bool seeded = cls & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), spill = cls & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
     const int nt = block_tile_count(a, w);
@@ -1311,6 +1335,21 @@ __global__ void __launch_bounds__(kTmaThreads * NG, 1) merge_all_tma_kernel(Merg
       }
     }
   }
+  if (a.peer.fused) {
+    // ---- after the pass: every consumer makes its peer stores visible, the pipeline meets, one thread counts the arrival;
+    //      the last arrival of the whole grid publishes the flag ----
+    const bool publish_ready = a.peer.has_next && ((pass == 0 && !a.peer.chained) || (pass == 2 && a.peer.chained));
+    const bool publish_ack = a.peer.has_prev && pass == 2;
+    if (publish_ready || publish_ack) {
+      __threadfence_system();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + pipe), "r"(kTmaConsumerWarps * 32) : "memory");
+      if (leader) {
+        if (publish_ready) peer_arrive_and_publish(a.peer.counters + (pass == 0 ? 0 : 2), arrivals, a.peer.next_ready, a.peer.epoch);
+        if (publish_ack) peer_arrive_and_publish(a.peer.counters + 1, arrivals, a.peer.prev_ack, a.peer.epoch);
+      }
+    }
+  }
+  }  // pass
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1980,6 +2019,21 @@ static int apply_merge_extra(const tb_merge_extra* ex, int raw, int K, float*& o
     a->peer.phase_mask = p.phase_mask; a->peer.t0 = p.t0; a->peer.t1 = p.t1;
     a->peer.seed_num = p.seed_num; a->peer.seed_den = p.seed_den; a->peer.seed_y0 = p.seed_y0; a->peer.seed_rows = p.seed_rows;
     a->peer.spill_num = p.spill_num; a->peer.spill_den = p.spill_den; a->peer.spill_y0 = p.spill_y0; a->peer.spill_rows = p.spill_rows;
+    a->peer.fused = p.fused ? 1 : 0;
+    if (p.fused) {
+      TB_REQUIRE(p.epoch > 0 && p.counters && p.timeout_ms > 0, TB_ERR_ARG, "tb_merge_all: fused peer plan needs epoch, counters, timeout");
+      TB_REQUIRE(!p.has_next || (p.next_ready && p.ack_flag && writes), TB_ERR_ARG, "tb_merge_all: fused plan with a next rank needs its flags and spill buffers");
+      TB_REQUIRE(!p.has_prev || (p.prev_ack && p.ready_flag && reads), TB_ERR_ARG, "tb_merge_all: fused plan with a previous rank needs its flags and seed buffers");
+      a->peer.chained = p.chained ? 1 : 0; a->peer.has_next = p.has_next ? 1 : 0; a->peer.has_prev = p.has_prev ? 1 : 0;
+      a->peer.epoch = p.epoch;
+      a->peer.counters = reinterpret_cast<unsigned long long*>(p.counters);
+      a->peer.ready_flag = reinterpret_cast<const unsigned long long*>(p.ready_flag);
+      a->peer.ack_flag = reinterpret_cast<const unsigned long long*>(p.ack_flag);
+      a->peer.next_ready = reinterpret_cast<unsigned long long*>(p.next_ready);
+      a->peer.prev_ack = reinterpret_cast<unsigned long long*>(p.prev_ack);
+      a->peer.status = reinterpret_cast<unsigned long long*>(p.status);
+      a->peer.timeout_ns = (long long)p.timeout_ms * 1000000ll;
+    }
   }
   return TB_OK;
 }

@@ -37,7 +37,49 @@ struct PeerPlan {
   float* spill_num;       // [K, spill_rows, Wp] (peer)
   float* spill_den;       // [spill_rows, Wp]    (peer)
   int spill_y0, spill_rows;
+  // FUSED mode (persistent TMA kernel only): ONE launch per step does all block classes in the order spill -> final -> seeded
+  // and handles the flags itself: before the first spill store it waits for `ack_flag >= epoch - 2` (the double buffer is
+  // free), after the last spill block of the whole grid it publishes `*next_ready = epoch`, before the first seeded block it
+  // waits for `ready_flag >= epoch`, after the last seeded block it publishes `*prev_ack = epoch`. `counters` = 3 local words
+  // that only ever grow (arrivals of the grid's pipelines; target = epoch * pipelines): no reset between launches.
+  int fused, chained, has_next, has_prev;
+  unsigned long long epoch;
+  unsigned long long* counters;            // local [3]: spill arrivals, seeded arrivals, chained-ready arrivals
+  const unsigned long long* ready_flag;    // local
+  const unsigned long long* ack_flag;      // local
+  unsigned long long* next_ready;          // peer (next rank's mailbox)
+  unsigned long long* prev_ack;            // peer (previous rank's mailbox)
+  unsigned long long* status;              // local: set when a wait timed out
+  long long timeout_ns;
 };
+
+// acquire-spin on a flag with a time-out (a dead neighbour must not hang the GPU); returns false on time-out
+__device__ __forceinline__ bool peer_spin_until(const unsigned long long* flag, unsigned long long value, long long timeout_ns,
+                                                unsigned long long* status) {
+  unsigned long long seen = 0;
+  long long start, now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    if (seen >= value) return true;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - start > timeout_ns) break;
+    __nanosleep(100);
+  }
+  if (status) *status = seen + 1ull;
+  return false;
+}
+
+// one thread per pipeline: count this pipeline's arrival; the LAST arrival of the grid publishes `value` to `flag`
+__device__ __forceinline__ void peer_arrive_and_publish(unsigned long long* counter, unsigned long long target, unsigned long long* flag,
+                                                        unsigned long long value) {
+  __threadfence_system();
+  const unsigned long long old = atomicAdd(counter, 1ull);
+  if (old + 1ull == target) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+  }
+}
 
 // Block class (0 = not ours / filtered out). (ra..rb, ca..cb) = ALL covering tile rows / columns of the block.
 __device__ __forceinline__ int peer_block_class(const PeerPlan& p, int nx, int ra, int rb, int ca, int cb) {

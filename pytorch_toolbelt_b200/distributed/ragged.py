@@ -94,9 +94,10 @@ class PeerMailbox:
     """This rank's receive side: two seed buffers (double-buffered over epochs) + the flag words, in ONE cudaMalloc'ed
     block that is exported to the neighbours with CUDA IPC.
 
-        word 0  ready   written by the PREVIOUS rank: seeds of epoch `ready` are complete (buffer epoch % 2)
-        word 1  ack     written by the NEXT rank: it has consumed the seeds of epoch `ack` that we stored into ITS mailbox
-        word 2  status  local: non-zero after a tb_peer_wait timed out
+        word 0    ready     written by the PREVIOUS rank: seeds of epoch `ready` are complete (buffer epoch % 2)
+        word 1    ack       written by the NEXT rank: it has consumed the seeds of epoch `ack` that we stored into ITS mailbox
+        word 2    status    local: non-zero after a flag wait timed out
+        word 3-5  counters  local: arrival counters of the fused single-launch mode (only ever grow)
     """
 
     HEADER = 256
@@ -120,6 +121,7 @@ class PeerMailbox:
     def ready(self, base=None): return (base or self.ptr) + 0
     def ack(self, base=None): return (base or self.ptr) + 8
     def status(self, base=None): return (base or self.ptr) + 16
+    def counters(self): return self.ptr + 24
     def num(self, parity: int, base=None): return (base or self.ptr) + self.HEADER + parity * self.buf_bytes
     def den(self, parity: int, base=None): return self.num(parity, base) + self.num_floats * 4
 
@@ -167,12 +169,17 @@ class RaggedMerger:
     """
 
     def __init__(self, engine, plan: RaggedPlan, preds, out: torch.Tensor, output: str = "logits", threshold: float = 0.5,
-                 exchange=None, timeout_ms: int = 5000):
+                 exchange=None, timeout_ms: int = 5000, fused: Optional[bool] = None):
         from .. import _native as N
 
         self.N, self.engine, self.plan, self.out = N, engine, plan, out
         self.timeout_ms = int(timeout_ms)
         self.epoch = 0
+        # fused: ONE merge launch per step, the kernel orders spill -> final -> seeded itself and handles the flags (persistent
+        # TMA kernel only, i.e. TTA groups with >= 2 views); otherwise two launches + stream-ordered flag kernels
+        self.fused = (engine.views > 1) if fused is None else bool(fused)
+        if self.fused and engine.views == 1:
+            raise ValueError("the fused single-launch mode needs the persistent TMA merge kernel (a TTA group with >= 2 views)")
         dev = engine.device
         hp, wp = engine.slicer.target_shape
         k = engine.channels
@@ -210,13 +217,37 @@ class RaggedMerger:
         # early as possible; (B) everything else -- FINAL and, after the wait for the previous rank's flag, the SEEDED blocks --
         # in ONE launch: by the time A has run here, the previous rank's A (same size, started at the same time) has run too,
         # so the wait in front of B costs nothing and a third launch (its ramp-up and tail) is saved.
-        self.spill = self.rest = (None, None)
+        self.spill = self.rest = self.one = (None, None)
+        self._fused_plans = []
+        if self.fused:
+            mask = PH_FINAL | (PH_SPILL if plan.next is not None else 0)
+            if plan.prev is not None:
+                mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
+            plans = []
+            for parity in (0, 1):
+                pd = peer(mask, parity)
+                pd.update(fused=1, chained=int(plan.chained), has_next=int(plan.next is not None), has_prev=int(plan.prev is not None),
+                          epoch=1, counters=mb.counters(), ready_flag=mb.ready(), ack_flag=mb.ack(),
+                          next_ready=mb.ready(self.next_base) if self.next_base else None,
+                          prev_ack=mb.ack(self.prev_base) if self.prev_base else None, status=mb.status(),
+                          timeout_ms=self.timeout_ms)
+                launch_plan = engine.merge_plan(preds, out=out, rows=(y0, y1), output=output, threshold=threshold,
+                                                first_tile=plan.t0, peer=pd)
+                plans.append(launch_plan)
+                self._fused_plans.append(pd["struct"])
+            self.one = tuple(plans)
+            return
         if plan.next is not None:
             self.spill = tuple(launch(PH_SPILL, (plan.spill_y0, plan.spill_y0 + win), p) for p in (0, 1))
         rest_mask = PH_FINAL
         if plan.prev is not None:  # (the last rank has nobody to spill to -- and no block of its range can need it)
             rest_mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
         self.rest = tuple(launch(rest_mask, (y0, y1), p) for p in (0, 1))
+        # the LAST rank has no spill launch to hide the neighbour's behind: it merges its unseeded blocks first and waits after
+        self.tail_final = self.tail_seeded = None
+        if plan.next is None and plan.prev is not None:
+            self.tail_final = tuple(launch(PH_FINAL, (y0, y1), p) for p in (0, 1))
+            self.tail_seeded = tuple(launch(PH_SEEDED_FINAL, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
 
     def run(self, marks=None):
         """One step (epoch): [wait ack] spill -> signal(ready) -> wait(ready) -> final + seeded [-> signal if chained] -> ack."""
@@ -225,6 +256,12 @@ class RaggedMerger:
         self.epoch += 1
         e, p = self.epoch, self.epoch % 2
         dev = self.engine.device
+        if self.fused:  # one launch: the kernel waits / publishes the flags itself
+            self._fused_plans[p].epoch = e
+            self.one[p].run()
+            if marks:
+                marks[0].record(torch.cuda.current_stream(dev))
+            return self.out
         with torch.cuda.device(dev):
             stream = N.stream_ptr(dev)
             if plan.next is not None:
@@ -236,10 +273,17 @@ class RaggedMerger:
                     N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
             if marks:  # (bench instrumentation: an event between the two halves of the step)
                 marks[0].record(torch.cuda.current_stream(dev))
-            if plan.prev is not None:
+            if self.tail_final is not None:
+                if self.tail_final[p] is not None:
+                    self.tail_final[p].run()
                 N.check(lib.tb_peer_wait(mb.ready(), e, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ready)")
-            if self.rest[p] is not None:
-                self.rest[p].run()
+                if self.tail_seeded[p] is not None:
+                    self.tail_seeded[p].run()
+            else:
+                if plan.prev is not None:
+                    N.check(lib.tb_peer_wait(mb.ready(), e, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ready)")
+                if self.rest[p] is not None:
+                    self.rest[p].run()
             if plan.next is not None and plan.chained:
                 N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
             if plan.prev is not None:

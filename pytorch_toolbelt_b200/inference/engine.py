@@ -343,8 +343,13 @@ class TiledInferenceEngine:
             peer_struct = N.PeerPlan(int(peer["phase_mask"]), int(peer["t0"]), int(peer["t1"]), peer.get("seed_num"),
                                      peer.get("seed_den"), int(peer.get("seed_y0", 0)), int(peer.get("seed_rows", 0)),
                                      peer.get("spill_num"), peer.get("spill_den"), int(peer.get("spill_y0", 0)),
-                                     int(peer.get("spill_rows", 0)))
+                                     int(peer.get("spill_rows", 0)),
+                                     int(peer.get("fused", 0)), int(peer.get("chained", 0)), int(peer.get("has_next", 0)),
+                                     int(peer.get("has_prev", 0)), int(peer.get("epoch", 0)), peer.get("counters"),
+                                     peer.get("ready_flag"), peer.get("ack_flag"), peer.get("next_ready"), peer.get("prev_ack"),
+                                     peer.get("status"), int(peer.get("timeout_ms", 5000)))
             keep.append(peer_struct)
+            peer["struct"] = peer_struct  # the caller advances `.epoch` before every run of a fused plan
             peer_ref = C.pointer(peer_struct)
         extra = N.MergeExtra(self._pre, self._temperature,
                              {"logits": TB.OUT_LOGITS, "labels": TB.OUT_ARGMAX, "mask": TB.OUT_MASK}[output], float(threshold),

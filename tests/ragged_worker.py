@@ -50,16 +50,26 @@ def main():
             view = own.view(eng.views, n_own, K, T, T)
             preds = [view[:, s : s + 7].reshape(-1, K, T, T).contiguous() for s in range(0, n_own, 7)]
         out = torch.full((K, shape[0], shape[1]), float("nan"), dtype=torch.float32, device=dev)
-        merger = RaggedMerger(eng, plan, preds, out, timeout_ms=20000)
-        for epoch in range(4):  # double-buffered seeds + acks: several epochs back to back without host synchronisation
-            out.fill_(float("nan"))
-            merger.run()
-        merger.check()
-        torch.save(out.cpu(), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
+        # multi-view cases run twice: fused single launch (in-kernel flags, the default) and two launches + flag kernels
+        results = []
+        for fused in ((None, False) if eng.views > 1 else (None,)):
+            merger = RaggedMerger(eng, plan, preds, out, timeout_ms=20000, fused=fused)
+            for epoch in range(4):  # double-buffered seeds + acks: several epochs back to back without host synchronisation
+                out.fill_(float("nan"))
+                merger.run()
+            merger.check()
+            results.append(out.clone())
+            dist.barrier()
+            merger.close()
+        if len(results) == 2:
+            same = torch.equal(torch.nan_to_num(results[0], nan=-1e30), torch.nan_to_num(results[1], nan=-1e30))
+            ok = ok and same
+            if not same:
+                print(f"rank {rank}: case {ci}: fused and two-launch results differ", flush=True)
+        torch.save(results[0].cpu(), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
         if rank == 0:
             torch.save(eng.merge(full.reshape(-1, K, T, T)).cpu(), os.path.join(out_dir, f"case{ci}_ref.pt"))
         dist.barrier()
-        merger.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
