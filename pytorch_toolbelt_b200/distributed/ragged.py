@@ -213,44 +213,26 @@ class RaggedMerger:
             return engine.merge_plan(preds, out=out, rows=rows, output=output, threshold=threshold,
                                      first_tile=plan.t0, peer=peer(mask, parity))
 
-        # Two merge launches per step: (A) the unseeded SPILL blocks first, so that the next rank's seeds are on their way as
-        # early as possible; (B) everything else -- FINAL and, after the wait for the previous rank's flag, the SEEDED blocks --
-        # in ONE launch: by the time A has run here, the previous rank's A (same size, started at the same time) has run too,
-        # so the wait in front of B costs nothing and a third launch (its ramp-up and tail) is saved.
-        self.spill = self.rest = self.one = (None, None)
-        self._fused_plans = []
-        if self.fused:
-            mask = PH_FINAL | (PH_SPILL if plan.next is not None else 0)
-            if plan.prev is not None:
-                mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
-            plans = []
-            for parity in (0, 1):
-                pd = peer(mask, parity)
-                pd.update(fused=1, chained=int(plan.chained), has_next=int(plan.next is not None), has_prev=int(plan.prev is not None),
-                          epoch=1, counters=mb.counters(), ready_flag=mb.ready(), ack_flag=mb.ack(),
-                          next_ready=mb.ready(self.next_base) if self.next_base else None,
-                          prev_ack=mb.ack(self.prev_base) if self.prev_base else None, status=mb.status(),
-                          timeout_ms=self.timeout_ms)
-                launch_plan = engine.merge_plan(preds, out=out, rows=(y0, y1), output=output, threshold=threshold,
-                                                first_tile=plan.t0, peer=pd)
-                plans.append(launch_plan)
-                self._fused_plans.append(pd["struct"])
-            self.one = tuple(plans)
-            return
+        # Unfused mode (single-view kernel, or fused=False): three launches -- SPILL, FINAL, SEEDED -- with the SPILL launch and
+        # its `ready` signal on a SIDE stream: the un-normalised overlap sums of a boundary are (K+1)(T-S)Wp*4 bytes of NVLink
+        # peer stores (26 MB at cfg 2, 84 MB at cfg 5 = ~93 us at 900 GB/s), which would otherwise sit exposed in front of the
+        # merge; on its own stream it overlaps the FINAL launch (HBM-bound, no dependence on anybody). The SEEDED launch follows
+        # FINAL behind the wait for the previous rank's flag -- by then that rank's spill has long landed.
+        self.spill = self.final = self.seeded = (None, None)
+        self.side = torch.cuda.Stream(dev) if plan.next is not None else None
+        self._ev_start = torch.cuda.Event()
+        self._ev_side = torch.cuda.Event()
         if plan.next is not None:
-            self.spill = tuple(launch(PH_SPILL, (plan.spill_y0, plan.spill_y0 + win), p) for p in (0, 1))
-        rest_mask = PH_FINAL
+            with torch.cuda.stream(self.side):  # PreparedLaunch binds the stream that is current when the plan is built
+                self.spill = tuple(launch(PH_SPILL, (plan.spill_y0, plan.spill_y0 + win), p) for p in (0, 1))
+        self.final = tuple(launch(PH_FINAL, (y0, y1), p) for p in (0, 1))
         if plan.prev is not None:  # (the last rank has nobody to spill to -- and no block of its range can need it)
-            rest_mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
-        self.rest = tuple(launch(rest_mask, (y0, y1), p) for p in (0, 1))
-        # the LAST rank has no spill launch to hide the neighbour's behind: it merges its unseeded blocks first and waits after
-        self.tail_final = self.tail_seeded = None
-        if plan.next is None and plan.prev is not None:
-            self.tail_final = tuple(launch(PH_FINAL, (y0, y1), p) for p in (0, 1))
-            self.tail_seeded = tuple(launch(PH_SEEDED_FINAL, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
+            seeded_mask = PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
+            self.seeded = tuple(launch(seeded_mask, (plan.seed_y0, plan.seed_y0 + win), p) for p in (0, 1))
 
     def run(self, marks=None):
-        """One step (epoch): [wait ack] spill -> signal(ready) -> wait(ready) -> final + seeded [-> signal if chained] -> ack."""
+        """One step (epoch). Fused: one launch. Otherwise: side stream: [wait ack] spill, signal(ready);  main stream: final,
+        wait(ready), seeded, [signal(ready) if chained], signal(ack), join the side stream."""
         N, plan, mb = self.N, self.plan, self.mailbox
         lib = N.lib()
         self.epoch += 1
@@ -263,29 +245,34 @@ class RaggedMerger:
                 marks[0].record(torch.cuda.current_stream(dev))
             return self.out
         with torch.cuda.device(dev):
-            stream = N.stream_ptr(dev)
+            main = torch.cuda.current_stream(dev)
+            stream = main.cuda_stream
             if plan.next is not None:
+                self._ev_start.record(main)
+                self.side.wait_event(self._ev_start)  # the predictions of this step are complete
+                side = self.side.cuda_stream
                 if e > 2:  # the next rank must have consumed the seeds of epoch e-2 before their buffer is overwritten
-                    N.check(lib.tb_peer_wait(mb.ack(), e - 2, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ack)")
+                    N.check(lib.tb_peer_wait(mb.ack(), e - 2, self.timeout_ms, mb.status(), side), "tb_peer_wait(ack)")
                 if self.spill[p] is not None:
                     self.spill[p].run()
                 if not plan.chained:
-                    N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
+                    N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, side), "tb_peer_signal(ready)")
+                    self._ev_side.record(self.side)
+            if self.final[p] is not None:
+                self.final[p].run()
             if marks:  # (bench instrumentation: an event between the two halves of the step)
-                marks[0].record(torch.cuda.current_stream(dev))
-            if self.tail_final is not None:
-                if self.tail_final[p] is not None:
-                    self.tail_final[p].run()
+                marks[0].record(main)
+            if plan.prev is not None:
                 N.check(lib.tb_peer_wait(mb.ready(), e, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ready)")
-                if self.tail_seeded[p] is not None:
-                    self.tail_seeded[p].run()
-            else:
-                if plan.prev is not None:
-                    N.check(lib.tb_peer_wait(mb.ready(), e, self.timeout_ms, mb.status(), stream), "tb_peer_wait(ready)")
-                if self.rest[p] is not None:
-                    self.rest[p].run()
-            if plan.next is not None and plan.chained:
-                N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
+                if self.seeded[p] is not None:
+                    self.seeded[p].run()
+            if plan.next is not None:
+                if plan.chained:  # seeded-AND-spilling blocks exist: the flag can only follow them (side-stream spill first)
+                    self._ev_side.record(self.side)
+                    main.wait_event(self._ev_side)
+                    N.check(lib.tb_peer_signal(mb.ready(self.next_base), e, stream), "tb_peer_signal(ready)")
+                else:
+                    main.wait_event(self._ev_side)  # the step is complete only when its spill has been handed over
             if plan.prev is not None:
                 N.check(lib.tb_peer_signal(mb.ack(self.prev_base), e, stream), "tb_peer_signal(ack)")
         return self.out
