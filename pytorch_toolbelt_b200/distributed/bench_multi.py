@@ -171,18 +171,22 @@ def run_multi_gpu(args, CFG, cfg_name, METRIC, UNIT, WORKLOAD):
                 "parallelism": f"ragged-strips{world}",
                 "halo_bytes_per_boundary": halo_bytes,
                 "collective": "none on the data path: the merge kernel stores the un-normalised (K+1) x (T-S) x Wp overlap sums of each range "
-                              "boundary into the next rank's seed buffer (NVLink peer stores, CUDA IPC) + 2 flags per boundary",
+                              "boundary into the next rank's seed buffer (NVLink peer stores, CUDA IPC) + 2 flags per boundary; "
+                              + ("ONE merge launch per rank and step, flags waited / published inside the kernel" if merger.fused else
+                                 "three merge launches per rank and step (spill on a side stream) + one-thread flag kernels"),
             },
             "with_model": {"value": mp / (ms_with_model * 1e-3), "unit": UNIT, "ms_per_step": ms_with_model},
             "phases_ms_max_over_ranks": {"slice": ms_slice, "merge_with_exchange": ms_merge},
             "phases_ms_inside_a_step": {"what": "CUDA events between the launches of one step, mean of 4 steps: [max over ranks, min over ranks]",
                                         "slice": [float(ph_max[0]), float(ph_min[0])],
-                                        "ack_wait+spill_merge+signal": [float(ph_max[1]), float(ph_min[1])],
-                                        "ready_wait+final_and_seeded_merge+ack": [float(ph_max[2]), float(ph_min[2])]},
+                                        "merge_first_half": [float(ph_max[1]), float(ph_min[1])],
+                                        "merge_second_half": [float(ph_max[2]), float(ph_min[2])],
+                                        "halves": "fused: [whole merge launch, nothing]; unfused: [final merge (spill on the side stream), "
+                                                  "flag wait + seeded merge + join]"},
             "e2e": {"value": mp / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(slab[0].item()), "d2h_bytes_per_step": int(slab[1].item()),
                     "api": "per rank: pinned host image SLAB -> slice / model / RaggedMerger on its tile range -> pinned host rows"},
-            "gpu_launches": (1 + 2 + 4) * args.steps,
+            "gpu_launches": (2 if merger.fused else 1 + 3 + 4) * args.steps,
             "roofline_step": {"algorithmic_bytes": b_alg, "achieved": b_alg / (ms_step * 1e-3) / 1e9, "peak": peak * world,
                               "frac": b_alg / (ms_step * 1e-3) / 1e9 / (peak * world), "unit": "GB/s",
                               "note": "whole-job algorithmic bytes / max-over-ranks step time / (N x measured single-GPU peak)"},
