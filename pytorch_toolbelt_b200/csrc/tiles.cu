@@ -2107,7 +2107,7 @@ int tb_merge_all_ex(const float* pred, const tb_grid* grid, int K, int tta, int 
                       (weight->kind != TB_W_TABLE || aligned16(weight->table));
   cudaStream_t s = (cudaStream_t)stream;
   // single view (no TTA): plain-load kernel, no staging (single_view.cu)
-  if (a.views.count == 1 && al && pred && !grid->tile_slot && single_view_enabled() && !tb_force_generic_merge()) {
+  if (a.views.count == 1 && !a.peer.fused && al && pred && !grid->tile_slot && single_view_enabled() && !tb_force_generic_merge()) {
     a.first_tile = 0;
     a.batch_tiles = grid->n_slots;
     a.covered_tiles = grid->n_slots;
@@ -2194,7 +2194,7 @@ int tb_merge_all_batched_ex(const float* const* batch_ptrs_host, int n_batches, 
   TB_REQUIRE(blocks > 0 && blocks < (1ll << 31), TB_ERR_ARG, "tb_merge_all_batched: grid too large");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaErrorInvalidValue;
-  if (a.views.count == 1 && single_view_enabled()) {
+  if (a.views.count == 1 && !a.peer.fused && single_view_enabled()) {
     BatchPtrs ptrs;
     for (int i = 0; i < n_batches; ++i) ptrs.p[i] = batch_ptrs_host[i];
     const int keep = a.batch_tiles;

@@ -218,7 +218,28 @@ class RaggedMerger:
         # peer stores (26 MB at cfg 2, 84 MB at cfg 5 = ~93 us at 900 GB/s), which would otherwise sit exposed in front of the
         # merge; on its own stream it overlaps the FINAL launch (HBM-bound, no dependence on anybody). The SEEDED launch follows
         # FINAL behind the wait for the previous rank's flag -- by then that rank's spill has long landed.
-        self.spill = self.final = self.seeded = (None, None)
+        self.spill = self.final = self.seeded = self.one = (None, None)
+        self._fused_plans = []
+        self.side = None
+        if self.fused:
+            # ONE launch per step: every block class of this rank in the mask, the kernel walks them in three ordered passes
+            # (spill, final, seeded) and waits for / publishes the flags itself (csrc/tiles.cu, merge_all_tma_kernel)
+            mask = PH_FINAL | (PH_SPILL if plan.next is not None else 0)
+            if plan.prev is not None:
+                mask |= PH_SEEDED_FINAL | (PH_SEEDED_SPILL if plan.next is not None else 0)
+            plans = []
+            for parity in (0, 1):
+                pd = peer(mask, parity)
+                pd.update(fused=1, chained=int(plan.chained), has_next=int(plan.next is not None),
+                          has_prev=int(plan.prev is not None), epoch=1, counters=mb.counters(), ready_flag=mb.ready(),
+                          ack_flag=mb.ack(), next_ready=mb.ready(self.next_base) if self.next_base else None,
+                          prev_ack=mb.ack(self.prev_base) if self.prev_base else None, status=mb.status(),
+                          timeout_ms=self.timeout_ms)
+                plans.append(engine.merge_plan(preds, out=out, rows=(y0, y1), output=output, threshold=threshold,
+                                               first_tile=plan.t0, peer=pd))
+                self._fused_plans.append(pd["struct"])  # `.epoch` is advanced before every run
+            self.one = tuple(plans)
+            return
         self.side = torch.cuda.Stream(dev) if plan.next is not None else None
         self._ev_start = torch.cuda.Event()
         self._ev_side = torch.cuda.Event()
