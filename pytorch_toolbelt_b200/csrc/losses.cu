@@ -13,6 +13,7 @@
 //   functional.py:250-277  wing_loss                         -> wing_kernel
 //   (Lovasz: csrc/lovasz.cu)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "loss_common.cuh"
@@ -61,6 +62,21 @@ __device__ __forceinline__ void focal_elem(const FocalDev& f, float x, float t, 
   if (p.has_ignore && t == p.ignore_index) {
     L = 0.f; dL = 0.f; F = 0.f; dF = 0.f;
   }
+}
+
+// FAST: the default BinaryFocalLoss() of BASELINE config 3 (gamma == 2, no alpha / class weights / ignore / reduced threshold):
+// closed forms, one ex2 + one rcp + one lg2 per element, no option branches. Same formulas as focal_elem, so the value
+// agrees with the general path to rounding (division by the MUFU reciprocal: <= 2 ulp on sigmoid).
+__device__ __forceinline__ void joint_elem_fast(float x, float t, float& pr, float& L, float& dL) {
+  const float e = __expf(-fabsf(x));
+  const float r = __fdividef(1.f, 1.f + e);
+  pr = x >= 0.f ? r : e * r;
+  const float ce = fmaxf(x, 0.f) - x * t + __logf(1.f + e);
+  const float base = pr + t - 2.f * pr * t;       // 1 - pt,  pt = p t + (1 - p)(1 - t)
+  const float focal = base * base;
+  const float dpt = pr * (1.f - pr) * (2.f * t - 1.f);
+  L = focal * ce;
+  dL = -2.f * base * dpt * ce + focal * (pr - t);
 }
 
 struct FocalArgs {
@@ -147,6 +163,60 @@ __global__ void __launch_bounds__(kLT) focal_kernel(FocalArgs a) {
       a.partials[2 * blockIdx.x] = acc[0];
       a.partials[2 * blockIdx.x + 1] = acc[1];
     }
+  }
+}
+
+// FAST single pass of the sigmoid focal loss for the default option set (gamma == 2, no class weights / ignore / reduced
+// threshold / normalisation; alpha optional): the closed forms of joint_elem_fast instead of focal_elem's option branches,
+// pow() and full-precision division -- the generic kernel is issue-bound (0.55 of the HBM peak at 134 M elements), this one
+// is back on the memory roofline. Float partial sums are flushed into the double accumulator every 4th vector.
+template <bool LABELS, bool ALPHA>
+__global__ void __launch_bounds__(kLT) focal_fast_kernel(FocalArgs a) {
+  const long long totalv = a.B * a.C * a.inner / 4;
+  const long long innerv = a.inner / 4;
+  const float al = a.f.p.alpha;
+  double acc[2] = {0.0, 0.0};
+  float part = 0.f;
+  int trips = 0;
+  for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < totalv; v += (long long)gridDim.x * kLT) {
+    float xs[4], tv[4], le[4], ge[4];
+    ld_vec<4>(a.x, v, xs);
+    if (LABELS) {
+      const long long row = v / innerv;
+      const long long posv = v - row * innerv;
+      const int c = (int)(row % a.C);
+      const long long* lp = static_cast<const long long*>(a.t) + (row / a.C) * a.inner + posv * 4;
+      const longlong2 l01 = __ldg(reinterpret_cast<const longlong2*>(lp)), l23 = __ldg(reinterpret_cast<const longlong2*>(lp) + 1);
+      tv[0] = l01.x == c ? 1.f : 0.f; tv[1] = l01.y == c ? 1.f : 0.f;
+      tv[2] = l23.x == c ? 1.f : 0.f; tv[3] = l23.y == c ? 1.f : 0.f;
+    } else {
+      ld_vec<4>(static_cast<const float*>(a.t), v, tv);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float pr, L, dL;
+      joint_elem_fast(xs[e], tv[e], pr, L, dL);
+      if (ALPHA) {
+        const float sc = al * tv[e] + (1.f - al) * (1.f - tv[e]);
+        L *= sc;
+        dL *= sc;
+      }
+      part += L;
+      le[e] = L;
+      ge[e] = dL * a.gscale;
+    }
+    if (a.loss_elem) st_vec<4>(a.loss_elem, v, le);
+    if (a.grad) st_vec<4>(a.grad, v, ge);
+    if ((++trips & 3) == 0) {
+      acc[0] += (double)part;
+      part = 0.f;
+    }
+  }
+  acc[0] += (double)part;
+  block_reduce<2>(acc);
+  if (threadIdx.x == 0) {
+    a.partials[2 * blockIdx.x] = acc[0];
+    a.partials[2 * blockIdx.x + 1] = 0.0;  // the focal-term sum only matters to the normalised loss (generic kernel)
   }
 }
 
@@ -668,7 +738,7 @@ __device__ __forceinline__ void region_class_terms(const tb_dice_params& p, cons
 #include "pixel_vec4.cuh"
 namespace tb {
 
-// VW: 1 / 4 = elementwise scalar / vector; 8 = multiclass with 4 pixels per thread (pixel_vec4.cuh), C <= 8
+// VW: 1 / 4 = elementwise scalar / vector; 8 / 12 = multiclass with 4 pixels per thread (pixel_vec4.cuh), C <= 8 / C <= 4
 template <int VW>
 __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
   extern __shared__ float sh_coef[];  // [C][2] alpha, beta (already divided by the number of averaged classes)
@@ -693,13 +763,13 @@ __global__ void __launch_bounds__(kLT) region_grad_kernel(RegionArgs a) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && a.loss_out) *a.loss_out = (float)sh_loss;
   if (!a.grad) return;
 
-  if (VW == 8) {
-    region_grad_mc_vec4<8>(a, sh_coef);
+  if (VW == 8 || VW == 12) {
+    region_grad_mc_vec4<VW == 8 ? 8 : 4>(a, sh_coef);
     return;
   }
   if (a.p.mode != 1) {
     // binary / multilabel: elementwise
-    constexpr int EV = VW == 8 ? 1 : VW;
+    constexpr int EV = VW >= 8 ? 1 : VW;
     const long long totalv = a.B * a.C * a.inner / EV, innerv = a.inner / EV;
     for (long long v = (long long)blockIdx.x * kLT + threadIdx.x; v < totalv; v += (long long)gridDim.x * kLT) {
       const int c = (int)((v / innerv) % a.C);
@@ -812,22 +882,7 @@ struct JointArgs {
   int chunks;
 };
 
-// shared by both passes so that they see identical p / loss terms
-// FAST: the default BinaryFocalLoss() of BASELINE config 3 (gamma == 2, no alpha / class weights / ignore / reduced threshold):
-// closed forms, one ex2 + one rcp + one lg2 per element, no option branches. Same formulas as focal_elem, so the value
-// agrees with the general path to rounding (division by the MUFU reciprocal: <= 2 ulp on sigmoid).
-__device__ __forceinline__ void joint_elem_fast(float x, float t, float& pr, float& L, float& dL) {
-  const float e = __expf(-fabsf(x));
-  const float r = __fdividef(1.f, 1.f + e);
-  pr = x >= 0.f ? r : e * r;
-  const float ce = fmaxf(x, 0.f) - x * t + __logf(1.f + e);
-  const float base = pr + t - 2.f * pr * t;       // 1 - pt,  pt = p t + (1 - p)(1 - t)
-  const float focal = base * base;
-  const float dpt = pr * (1.f - pr) * (2.f * t - 1.f);
-  L = focal * ce;
-  dL = -2.f * base * dpt * ce + focal * (pr - t);
-}
-
+// shared by both passes so that they see identical p / loss terms (joint_elem_fast: above, next to focal_elem)
 __device__ __forceinline__ void joint_elem(const JointArgs& a, float x, float t, int c, float& pr, float& L, float& dL) {
   const float ex = __expf(-fabsf(x));
   const float inv = 1.f / (1.f + ex);
@@ -1138,7 +1193,21 @@ int tb_focal_fwd_bwd(const float* x, const void* t, int t_kind, int64_t B, int C
       focal_kernel<PASS, false, 1><<<grid, kLT, 0, s>>>(a);              \
   } while (0)
   float* scalar_out = (elem_out || batchwise) ? nullptr : loss_out;
-  if (!p->normalized) {
+  // default option set -> closed-form kernel (TB200_FOCAL_GENERIC=1 keeps the generic one: A/B and parity tests)
+  static const bool force_generic = getenv("TB200_FOCAL_GENERIC") && atoi(getenv("TB200_FOCAL_GENERIC")) != 0;
+  const bool labels16 = !labels || (inner % 4 == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0);
+  const bool fast = vec4 && labels16 && !p->normalized && p->gamma == 2.f && !class_w && !p->has_ignore && !p->has_reduced_threshold &&
+                    !force_generic;
+  if (fast) {
+    if (labels) {
+      if (p->has_alpha) focal_fast_kernel<true, true><<<grid, kLT, 0, s>>>(a);
+      else focal_fast_kernel<true, false><<<grid, kLT, 0, s>>>(a);
+    } else {
+      if (p->has_alpha) focal_fast_kernel<false, true><<<grid, kLT, 0, s>>>(a);
+      else focal_fast_kernel<false, false><<<grid, kLT, 0, s>>>(a);
+    }
+    focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, scalar_out, p->reduction, 0, p->eps, numel);
+  } else if (!p->normalized) {
     TB_FOCAL_LAUNCH(0);
     focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, grid, sums, scalar_out, p->reduction, 0, p->eps, numel);
   } else {
@@ -1190,8 +1259,13 @@ int tb_softmax_focal_fwd_bwd(const float* x, const int64_t* t, int64_t B, int C,
     const int gq = loss_grid(B * inner / 4);
     a.partials = partials;
     double* sums_q = partials + 2 * (size_t)gq;
-    if (C <= 4) softmax_focal_vec4_kernel<4><<<gq, kLT, 0, s>>>(a);
-    else softmax_focal_vec4_kernel<8><<<gq, kLT, 0, s>>>(a);
+    const bool g2 = gamma == 2.f && !class_w;  // the defaults: no pow(), smaller register budget
+    static const int minb = getenv("TB200_SFOCAL_MINB") ? atoi(getenv("TB200_SFOCAL_MINB")) : 3;  // A/B: register budget
+    if (C <= 4 && g2 && minb == 4) softmax_focal_vec4_kernel<4, true, 4><<<gq, kLT, 0, s>>>(a);
+    else if (C <= 4 && g2) softmax_focal_vec4_kernel<4, true, 3><<<gq, kLT, 0, s>>>(a);
+    else if (C <= 4) softmax_focal_vec4_kernel<4, false, 1><<<gq, kLT, 0, s>>>(a);
+    else if (g2) softmax_focal_vec4_kernel<8, true, 1><<<gq, kLT, 0, s>>>(a);
+    else softmax_focal_vec4_kernel<8, false, 1><<<gq, kLT, 0, s>>>(a);
     focal_finalize_kernel<<<1, kLT, 0, s>>>(partials, gq, sums_q, scalar_out, reduction, 0, eps, npos);
   } else if (!normalized) {
     launch_pixel_focal<0>(a, grid, s);
@@ -1225,9 +1299,9 @@ int tb_dice_stats(const float* x, const void* t, int t_kind, int64_t B, int C, i
     const bool quads = (inner % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(t) & 15) == 0 && C <= 8;
     const int grid = loss_grid(quads ? B * inner / 4 : B * inner);
     if (quads && C <= 4)
-      region_stats_mc_vec4_kernel<4><<<grid, kLT, 0, s>>>(a);
+      region_stats_mc_vec4_kernel<4, true><<<grid, kLT, 0, s>>>(a);
     else if (quads)
-      region_stats_mc_vec4_kernel<8><<<grid, kLT, 0, s>>>(a);
+      region_stats_mc_vec4_kernel<8, false><<<grid, kLT, 0, s>>>(a);
     else if (C <= 4)
       region_stats_mc_small_kernel<4><<<grid, kLT, 0, s>>>(a);
     else if (C <= 8)
@@ -1277,7 +1351,9 @@ int tb_dice_loss_grad(const float* x, const void* t, int t_kind, int64_t B, int 
       grid = loss_grid(B * C * inner / (vec4 ? 4 : 1));
     }
   }
-  if (mc_quads)
+  if (mc_quads && C <= 4)
+    region_grad_kernel<12><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
+  else if (mc_quads)
     region_grad_kernel<8><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);
   else if (vec4)
     region_grad_kernel<4><<<grid, kLT, 2 * C * sizeof(float), s>>>(a);

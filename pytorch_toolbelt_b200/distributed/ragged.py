@@ -18,6 +18,7 @@ Ownership rule: a canvas pixel belongs to the rank that owns its LAST covering t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -177,6 +178,8 @@ class RaggedMerger:
         self.epoch = 0
         # fused: ONE merge launch per step, the kernel orders spill -> final -> seeded itself and handles the flags (persistent
         # TMA kernel only, i.e. TTA groups with >= 2 views); otherwise two launches + stream-ordered flag kernels
+        if fused is None and os.environ.get("TB200_RAGGED_FUSED") in ("0", "1"):  # A/B switch for the benchmarks
+            fused = os.environ["TB200_RAGGED_FUSED"] == "1" and engine.views > 1
         self.fused = (engine.views > 1) if fused is None else bool(fused)
         if self.fused and engine.views == 1:
             raise ValueError("the fused single-launch mode needs the persistent TMA merge kernel (a TTA group with >= 2 views)")
