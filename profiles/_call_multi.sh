@@ -14,11 +14,11 @@ run() {  # run <config> <tag> : one torchrun bench
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --config $c --steps 20 --warmup 3 > gpurun_out/r2/scale_${c}_n${N}${tag}.json 2> gpurun_out/r2/scale_${c}_n${N}${tag}.err; echo "bench $c N=$N $tag rc=$?"
   python -c "
 import json
-d=json.load(open('gpurun_out/r2/scale_${c}_n${N}${tag}.json'))
+d=json.loads([l for l in open('gpurun_out/r2/scale_${c}_n${N}${tag}.json') if l.startswith('{')][-1])
 print('$c$tag', 'N', d['n_gpus'], 'value', round(d['value']), 'ms', round(d['ms_per_step'],4), 'phases', d.get('phases_ms_max_over_ranks'), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline_step']['frac'],3))
 " || tail -5 gpurun_out/r2/scale_${c}_n${N}${tag}.err
 }
 for c in $CFGS; do
   run $c _fused
-  if [ "$c" != "cfg5" ]; then TB200_RAGGED_FUSED=0 run $c _unfused; fi
+  if [ "$c" != "cfg5" ] && [ "$AB" = "1" ]; then TB200_RAGGED_FUSED=0 run $c _unfused; fi
 done

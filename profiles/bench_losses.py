@@ -54,7 +54,10 @@ cases = {
     "wing": (lambda z: L.WingLoss()(z, t), lambda z: LO.wing_loss(z, t), 3 * N * 4),
 }
 out = {"config": "cfg3: 32x4x1024x1024 f32 logits, fwd+bwd to x.grad", "peak_gbs": peak, "cases": {}}
+only = set(sys.argv[1:])  # optional case filter
 for name, (ours, ref, alg_bytes) in cases.items():
+    if only and name not in only:
+        continue
     try:
         ms_ours = timed(fwd_bwd(ours))
     except Exception as e:  # an experimental kernel must not take the other measurements down with it
