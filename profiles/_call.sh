@@ -1,19 +1,16 @@
-# loss kernels: parity with the closed-form focal kernel (default) and the generic one, A/B timing, launch list, ncu --set full
+# last GPU call of the round: parity + timing of the shared-memory separable gaussian (cfg 5), ncu launch list and full capture of cfg 2
 set -x
 cd $GRAFT_REPO_ROOT
-mkdir -p gpurun_out/r2
-timeout 600 python -m pytest tests/test_losses_gpu.py tests/test_joint_labels_gpu.py tests/test_losses_extra_gpu.py tests/test_full_size_gpu.py -q --timeout 500 -k "loss or focal or cfg3 or joint" > gpurun_out/r2/tests_losses_fast.log 2>&1; echo "losses (fast focal) rc=$?"
-tail -3 gpurun_out/r2/tests_losses_fast.log
-TB200_FOCAL_GENERIC=1 timeout 600 python -m pytest tests/test_losses_gpu.py -q --timeout 500 > gpurun_out/r2/tests_losses_generic.log 2>&1; echo "losses (generic focal) rc=$?"
-tail -3 gpurun_out/r2/tests_losses_generic.log
-timeout 600 python profiles/bench_losses.py > gpurun_out/r2/losses_cfg3_c.json 2> gpurun_out/r2/losses_cfg3_c.err; echo "bench_losses rc=$?"
-TB200_FOCAL_GENERIC=1 timeout 600 python profiles/bench_losses.py > gpurun_out/r2/losses_cfg3_c_generic_focal.json 2>/dev/null
-python - <<'EOF'
-import json
-for f in ("losses_cfg3_c", "losses_cfg3_c_generic_focal"):
-    d = json.load(open(f"gpurun_out/r2/{f}.json"))
-    print(f, {k: (v.get("ours_ms"), v.get("frac_of_measured_peak")) for k, v in d["cases"].items()})
-EOF
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2/launches_losses.csv python profiles/prof_losses.py > gpurun_out/r2/launches_losses.log 2>&1; echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'softmax_focal_vec4|region_stats_mc|region_grad|focal_fast|focal_kernel|region_stats_elem_kernel' --launch-skip 6 -c 6 -o gpurun_out/r2/prof_losses_c -f python profiles/prof_losses.py > gpurun_out/r2/ncu_losses_c.log 2>&1; echo "ncu rc=$?"
-ls -la gpurun_out/r2 | tail -12
+O=gpurun_out/r2/final
+mkdir -p $O
+timeout 300 python -m pytest tests/test_merge_options_gpu.py tests/test_full_size_gpu.py tests/test_engine_gpu.py -q --timeout 250 -k "single_view or cfg5 or analytic or cfg1" > $O/tests_single_view.log 2>&1; echo "single-view tests rc=$?"
+tail -2 $O/tests_single_view.log
+timeout 200 python profiles/bench_configs.py cfg5 cfg5_table_weight cfg1 > $O/configs_smem_gauss.json 2>/dev/null; echo "rc=$?"; cat $O/configs_smem_gauss.json
+TB200_SV_GAUSS=1 timeout 200 python profiles/bench_configs.py cfg5 > $O/configs_register_gauss.json 2>/dev/null; cat $O/configs_register_gauss.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_cfg2.csv python bench.py --steps 2 --warmup 1 > $O/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
+timeout 300 ncu --set full --clock-control none -k regex:'merge_all_tma|slice_augment_fast' --launch-skip 2 -c 2 -o /tmp/prof_cfg2 -f python profiles/prof_tiles.py 2 > $O/ncu_cfg2.log 2>&1; echo "ncu cfg2 rc=$?"
+ncu -i /tmp/prof_cfg2.ncu-rep --page raw --csv > $O/prof_cfg2.raw.csv 2>/dev/null
+timeout 200 ncu --set full --clock-control none -k regex:'merge_single_view|slice_u8c1' --launch-skip 4 -c 2 -o /tmp/prof_cfg5 -f python profiles/bench_configs.py cfg5 > $O/ncu_cfg5.log 2>&1; echo "ncu cfg5 rc=$?"
+ncu -i /tmp/prof_cfg5.ncu-rep --page raw --csv > $O/prof_cfg5.raw.csv 2>/dev/null
+timeout 300 python bench.py --config cfg5 --steps 10 --warmup 3 > $O/bench_cfg5.json 2> $O/bench_cfg5.err; echo "bench cfg5 rc=$?"; cut -c1-400 $O/bench_cfg5.json
+du -sh gpurun_out

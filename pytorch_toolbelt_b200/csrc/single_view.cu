@@ -34,7 +34,8 @@ __device__ __forceinline__ void ldcs4(const float* p, float v[4]) {
 // merge
 // ---------------------------------------------------------------------------------------------------------------
 // UW = unit width in pixels (128: Tw and Sx multiples of 128; 32 otherwise).
-// WK = how the tile weight is obtained: 0 table (L2-resident), 1 separable in-register gaussian, 2 weight_at() per pixel.
+// WK = how the tile weight is obtained: 0 table (L2-resident), 1 separable gaussian (column factors in registers), 2 weight_at()
+//      per pixel, 3 separable gaussian with the unit's 1-D factors in shared memory (default for gaussian weights).
 // PLAIN: mean / sum reduction and no pre-activation (one view: the value itself): no per-element switch.
 // gridDim.y > 1: one row pass per CTA (small problems: 4x the CTAs, a quarter of the dependent load rounds per CTA).
 //
@@ -96,10 +97,30 @@ __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllAr
   __syncthreads();
   const int nt = s_nt, cls = s_cls;
   if (nt < 0) return;
+  // WK == 3: separable gaussian with the 1-D factors of the unit's covering tiles in shared memory -- per listed tile 32 row
+  // factors exp(-di^2 c) and UW column factors exp(-dj^2 c), computed once per CTA by all threads (<= 3 ex2 each); the inner
+  // loop then costs one LDS.32 + one LDS.128 + 4 FMUL per tile instead of an L2 round trip (table) or 16 live registers of
+  // column factors + one ex2 per tile (WK == 1, which pushed the 64-register instance into spills).
+  __shared__ float s_wi[WK == 3 ? 4 : 1][WK == 3 ? 32 : 1];
+  __shared__ __align__(16) float s_wj[WK == 3 ? 4 : 1][WK == 3 ? UW : 1];
+  if constexpr (WK == 3) {
+    const int ntl = min(nt, 4);
+    for (int idx = threadIdx.x; idx < ntl * (32 + UW); idx += kSV) {
+      const int u = idx / (32 + UW), r = idx - u * (32 + UW);
+      if (r < 32) {
+        const float di = (float)(Y0 + r - s_ty[u]) - a.w.hc;
+        s_wi[u][r] = __expf(-(di * di) * a.w.param);
+      } else {
+        const float dj = (float)(X0 + (r - 32) - s_tx[u]) - a.w.wc;
+        s_wj[u][r - 32] = __expf(-(dj * dj) * a.w.param);
+      }
+    }
+    __syncthreads();
+  }
   const bool seeded = cls & (TB_PH_SEEDED_FINAL | TB_PH_SEEDED_SPILL), spill = cls & (TB_PH_SPILL | TB_PH_SEEDED_SPILL);
   const int lc = threadIdx.x % LPR, row0 = threadIdx.x / LPR;
   const int x = X0 + 4 * lc;
-  if (x >= a.Wp) return;  // (after the only barrier)
+  if (x >= a.Wp) return;  // (after the last barrier)
   const int rows = a.y1 - a.y0;
 
   // separable gaussian: w(i,j) = exp(-di^2 c) * exp(-dj^2 c); the column factors of the first four listed tiles live in
@@ -151,6 +172,10 @@ __global__ void __launch_bounds__(kSV, MINB) merge_single_view_kernel(MergeAllAr
             if (WK == 0) {
               const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w.table + off));
               wv[u][0] = w4.x; wv[u][1] = w4.y; wv[u][2] = w4.z; wv[u][3] = w4.w;
+            } else if (WK == 3) {  // (only launched with nt <= 4)
+              const float wi = s_wi[u0 + u][y - Y0];
+              const float4 w4 = *reinterpret_cast<const float4*>(&s_wj[u0 + u][4 * lc]);
+              wv[u][0] = wi * w4.x; wv[u][1] = wi * w4.y; wv[u][2] = wi * w4.z; wv[u][3] = wi * w4.w;
             } else if (WK == 1) {
               const float di = (float)i - a.w.hc;
               const float wi = __expf(-(di * di) * a.w.param);
@@ -210,7 +235,8 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   const int uw = wide ? 128 : 32;
   const int cover = ((g.Tw + g.Sx - 1) / g.Sx) * ((g.Th + g.Sy - 1) / g.Sy);
   if (cover > kSvMaxTiles) return cudaErrorNotSupported;
-  const int wk = a.w.kind == TB_W_TABLE ? 0 : ((a.w.kind == TB_W_GAUSSIAN && cover <= 4) ? 1 : 2);
+  static const int gauss_variant = getenv("TB200_SV_GAUSS") ? atoi(getenv("TB200_SV_GAUSS")) : 3;  // 3: smem factors, 1: registers
+  const int wk = a.w.kind == TB_W_TABLE ? 0 : ((a.w.kind == TB_W_GAUSSIAN && cover <= 4) ? (gauss_variant == 1 ? 1 : 3) : 2);
   const bool plain = (a.red == TB_RED_MEAN || a.red == TB_RED_SUM) && a.pre == TB_PRE_NONE;
   const int xa = a.raw ? 0 : a.left, xb = a.raw ? a.Wp : a.left + a.W;
   const int ux0 = xa / uw, nux = (xb + uw - 1) / uw - ux0;
@@ -224,7 +250,7 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
   // per SM (default 44: 4 tiles in flight, 4 CTAs/SM = 64 registers; measured on cfg 5, profiles/r2_single_view_variants.md)
   const char* mv = getenv("TB200_SV_MERGE");
   const int var = mv ? atoi(mv) : 44;
-  if (wide && plain && wk <= 1 && var != 44) {
+  if (wide && plain && (wk <= 1 || wk == 3) && var != 44) {
 #define TB_SV_MB(WK_, MB, CH_) merge_single_view_kernel<128, WK_, true, MB, CH_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
 #define TB_SV_VAR(WK_)                                                          \
     switch (var) {                                                              \
@@ -234,13 +260,13 @@ cudaError_t launch_merge_single_view(const MergeAllArgs& a, const BatchPtrs& ptr
       case 26: TB_SV_MB(WK_, 6, 2); break;                                      \
       default: TB_SV_MB(WK_, 4, 4); break;                                      \
     }
-    if (wk == 0) { TB_SV_VAR(0) } else { TB_SV_VAR(1) }
+    if (wk == 0) { TB_SV_VAR(0) } else if (wk == 3) { TB_SV_VAR(3) } else { TB_SV_VAR(1) }
 #undef TB_SV_VAR
 #undef TB_SV_MB
     return cudaGetLastError();
   }
 #define TB_SV(UW, WK_, PLAIN_) merge_single_view_kernel<UW, WK_, PLAIN_><<<grid, kSV, 0, s>>>(a, ptrs, nux, ux0)
-#define TB_SV_WK(UW, PLAIN_) do { if (wk == 0) TB_SV(UW, 0, PLAIN_); else if (wk == 1) TB_SV(UW, 1, PLAIN_); else TB_SV(UW, 2, PLAIN_); } while (0)
+#define TB_SV_WK(UW, PLAIN_) do { if (wk == 0) TB_SV(UW, 0, PLAIN_); else if (wk == 1) TB_SV(UW, 1, PLAIN_); else if (wk == 3) TB_SV(UW, 3, PLAIN_); else TB_SV(UW, 2, PLAIN_); } while (0)
   if (wide) {
     if (plain) TB_SV_WK(128, true); else TB_SV_WK(128, false);
   } else {
