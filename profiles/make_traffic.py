@@ -18,7 +18,10 @@ UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
 def rows_of(path):
-    text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):  # already exported on the GPU box (`ncu -i rep --page raw --csv`): the .ncu-rep stayed there
+        text = open(path).read()
+    else:
+        text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     lines = [ln for ln in text.splitlines() if ln.startswith('"')]
     return list(csv.reader(io.StringIO("\n".join(lines))))
 

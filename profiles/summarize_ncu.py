@@ -48,7 +48,10 @@ def launches(path):
 
 
 def full(path, pattern=None):
-    text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):  # exported on the GPU box with `ncu -i rep --page raw --csv`
+        text = open(path).read()
+    else:
+        text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = _rows(text)
     head, units = rows[0], rows[1]
     name_i = head.index("Kernel Name")
