@@ -10,8 +10,12 @@ row strips of ``strips.py`` (round 1):
   un-normalised into the NEXT rank's seed buffer (CUDA-IPC mapped peer memory, ``tb_peer_*``), and finished there starting
   from that seed. The accumulation order is the single-GPU tile order, so the sharded result is bit-identical;
 * ordering: two uint64 flags per boundary (``ready``: seeds of epoch e are complete; ``ack``: seeds of epoch e were consumed,
-  the double buffer may be reused), written / awaited by one-thread kernels in stream order (``tb_peer_signal/wait``): the
-  host never blocks, a step is 3 merge launches + <= 4 flag launches per rank.
+  the double buffer may be reused). FUSED form (persistent TMA merge kernel, TTA groups with >= 2 views; the default there):
+  ONE merge launch per rank and step -- the kernel walks its blocks in three ordered passes (spill, final, seeded), one thread
+  per pipeline waits for ``ack`` / ``ready`` in front of the pass that needs it, and the LAST pipeline of the grid to finish a
+  pass publishes the neighbour's flag. UNFUSED form (single-view kernel, or ``fused=False``): three merge launches, the spill
+  and its ``ready`` signal on a side stream, one-thread ``tb_peer_signal/wait`` kernels in stream order. The host never blocks.
+  Measured (profiles/r2_scaling_summary.md): cfg 2 at 8 GPUs 0.570 ms fused against 0.602 (two launches) / 0.658 (three).
 
 Ownership rule: a canvas pixel belongs to the rank that owns its LAST covering tile (row-major order).
 """
