@@ -38,3 +38,21 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_capture():
+    """bench.py's `roofline.traffic` for the contract config is read from profiles/traffic.json (made from the ncu capture
+    by profiles/make_traffic.py) and must sit within 1 % of the algorithmic bytes of the merge kernel: nothing is re-read."""
+    sys.path.insert(0, REPO)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    traffic, source = bench.measured_traffic("cfg2", "merge_all_tma_kernel")
+    assert traffic is not None and "ncu" in source
+    cfg = bench.CONFIGS["cfg2"]
+    H, W, T, S, K = (cfg[k] for k in ("H", "W", "T", "S", "K"))
+    n_side = -(-(H - T) // S) + 1
+    tiles = n_side * n_side
+    algorithmic = tiles * 8 * K * T * T * 4 + K * H * W * 4  # 8 D4 views of every tile's logits in, the cropped canvas out
+    assert tiles == 361 and abs(traffic / algorithmic - 1.0) < 0.01
+    assert bench.measured_traffic("cfg2", "no_such_kernel") == (None, None)
